@@ -1,0 +1,161 @@
+/* vqb200.h -- C ABI of the B200-native vector-quantisation bottleneck (libvqb200.so, sm_100a only).
+ *
+ * Drop-in boundary for ONE path of vliu15/speech-masters-thesis: models/vqvae/bottleneck.py.
+ * The reference has no FFI layer (it is pure PyTorch); every entry point below cites the reference
+ * lines whose work it replaces.  The Python module speech-masters-thesis_b200/bottleneck.py binds these
+ * with ctypes (tensor.data_ptr(), torch.cuda.current_stream().cuda_stream) and keeps the reference's
+ * nn.Module surface; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; vq_last_error() gives the message
+ *     (thread-local, valid until the next failing call on that thread).  No exception crosses the ABI.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; nothing is allocated or freed
+ *     behind the caller's back except inside a vq_host_ctx.
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise
+ *     (the *_host entry points are the exception: they return when the host buffers are filled).
+ *   - latents x / x_q / grad tensors are [N, D, T] fp32, T contiguous ("NCT", the layout the reference's
+ *     encoder emits, bottleneck.py:92-95); indices are [N, T] int64; mask is [N, 1, T] fp32 (== [N*T]);
+ *     the codebook is [K, D] fp32 row-major (buffer `k`, bottleneck.py:24).
+ *   - there is no CPU fallback.  On a machine without an sm_100 GPU the compute calls fail with an error.
+ */
+#ifndef VQB200_H
+#define VQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB200_VERSION 100
+
+/* ---- algorithm selector for vq_assign --------------------------------------------------------- */
+enum {
+    VQ_ALGO_AUTO = 0,   /* tcgen05 path when the shape allows it, else the SIMT path                   */
+    VQ_ALGO_SIMT = 1,   /* exact-FP32 register-tiled CUDA-core kernel (any shape)                      */
+    VQ_ALGO_TC   = 2    /* BF16 tcgen05/TMEM distance GEMM + top-2 + FP32 rescoring (+ exact fallback) */
+};
+
+/* ---- scalar slots (fp64 accumulators in caller-owned device memory, VQ_NUM_SCALARS doubles) --- */
+enum {
+    VQ_S_SUM_MIN_D   = 0,   /* sum over ALL rows of the winning distance  (fit * K, bottleneck.py:140)  */
+    VQ_S_COMMIT_SQ   = 1,   /* sum over valid rows of ||e - x||^2         (bottleneck.py:194)           */
+    VQ_S_MASK_SUM    = 2,   /* sum of the mask                            (bottleneck.py:194)           */
+    VQ_S_UNSAFE_ROWS = 3,   /* rows the tcgen05 path handed to the exact fallback (diagnostic)          */
+    VQ_S_COUNT_TOTAL = 4,   /* sum of the (all-reduced) per-code counts   (bottleneck.py:85)            */
+    VQ_S_ENTROPY     = 5,
+    VQ_S_USED_CURR   = 6,
+    VQ_S_USAGE       = 7,
+    VQ_S_DK_SQ       = 8,
+    VQ_S_TICKET      = 9,   /* last-block tickets */
+    VQ_NUM_SCALARS   = 16
+};
+
+/* ---- float outputs written by the finishing blocks (VQ_NUM_RESULTS floats) -------------------- */
+enum {
+    VQ_R_FIT = 0,        /* bottleneck.py:140 */
+    VQ_R_COMMIT = 1,     /* bottleneck.py:194 */
+    VQ_R_ENTROPY = 2,    /* bottleneck.py:86  */
+    VQ_R_USAGE = 3,      /* bottleneck.py:88  */
+    VQ_R_DK = 4,         /* bottleneck.py:89  */
+    VQ_R_USED_CURR = 5,  /* bottleneck.py:87 (exact small integer stored as float; also as int64, see finalize) */
+    VQ_NUM_RESULTS = 8
+};
+
+int         vq_version(void);
+const char* vq_last_error(void);
+/* 1 when the current device can run the tcgen05 kernels (compute capability 10.x), else 0. */
+int         vq_device_supported(void);
+
+/* Bytes of scratch vq_assign needs for this shape (BF16 codebook image, norms, fallback worklist). */
+size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_width);
+
+/* K1 -- replaces BottleneckBlock.preprocess + quantize (bottleneck.py:92-100,126-141) and, for the
+ * generate script, BottleneckBlock.encode (bottleneck.py:147-158; caller scripts/generate_vq_dataset.py:69).
+ *   x [N,D,T] fp32, k [K,D] fp32  ->  idx [N*T] int64 (argmin, lowest index on ties),
+ *   min_d [N*T] fp32 or NULL, scalars[VQ_S_SUM_MIN_D] += sum(min_d) (scalars may be NULL).
+ * The distance is ||x||^2 - 2 x.e + ||e||^2 evaluated in FP32 for the winner exactly as the reference
+ * expression does; the tcgen05 path only uses BF16 to shortlist candidates. */
+int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+              const float* k, int k_bins,
+              int64_t* idx, float* min_d, double* scalars,
+              void* workspace, size_t workspace_bytes, int algo, void* stream);
+
+/* K2 forward -- replaces dequantize + commit loss + straight-through + postprocess + mask multiply
+ * (bottleneck.py:143-145,194,197,118-124,201).
+ *   x_q[n,d,t] = (x + (k[idx] - x)) * mask      (same two FP32 roundings as the reference expression)
+ *   scalars[VQ_S_COMMIT_SQ] += sum_{mask!=0} ||k[idx]-x||^2 ; scalars[VQ_S_MASK_SUM] += sum(mask)
+ *   the last block writes results[VQ_R_COMMIT] = COMMIT_SQ / (MASK_SUM * D) and
+ *   results[VQ_R_FIT] = SUM_MIN_D / K.  mask may be NULL (all ones). */
+int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k,
+                     int64_t n_utt, int64_t emb_width, int64_t t_frames, int k_bins,
+                     float* x_q, double* scalars, float* results, void* stream);
+
+/* K2 backward -- the autograd contract of bottleneck.py:194-201: only x receives gradient,
+ *   grad_x = mask * grad_xq + [mask!=0] * grad_commit * 2 (x - k[idx]) / (MASK_SUM * D).
+ * grad_commit is a device scalar; scalars[VQ_S_MASK_SUM] must still hold the forward's value.
+ * grad_xq may be NULL (treated as zero). */
+int vq_gather_st_bwd(const float* x, const int64_t* idx, const float* mask, const float* k,
+                     const float* grad_xq, const float* grad_commit, const double* scalars,
+                     int64_t n_utt, int64_t emb_width, int64_t t_frames, int k_bins,
+                     float* grad_x, void* stream);
+
+/* Decode -- replaces BottleneckBlock.decode (bottleneck.py:160-169; callers
+ * scripts/generate_vq_dataset.py:75, models/transformer_lm/transformer_lm.py:103): idx [N,T] -> [N,D,T]. */
+int vq_decode(const int64_t* idx, const float* k, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+              int k_bins, float* x_d, void* stream);
+
+/* K3a -- replaces the dense one-hot scatter + GEMM + row-sum of update_k (bottleneck.py:64-68).
+ *   stats is [K*D + K] fp32: per-code sums of the valid rows followed by per-code counts.
+ *   The call ADDS into stats (zero it first); it is the buffer the caller all-reduces over NCCL
+ *   (bottleneck.py:74-75) before vq_ema_finalize. */
+int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask,
+                      int64_t n_utt, int64_t emb_width, int64_t t_frames, int k_bins,
+                      float* stats, void* stream);
+
+/* K3b -- replaces the EMA lerp, usage threshold, dead-code revival and the four metrics of update_k
+ * (bottleneck.py:78-89).  k_sum, k_elem are updated in place; the new codebook is written to k, which may
+ * alias k_old (the reference rebinds self.k to a fresh tensor every step, and autograd may still hold the
+ * old one, so the Python module passes a fresh buffer); k_rand [K,D] holds the restart rows
+ * (bottleneck.py:69-70,73).  results[VQ_R_ENTROPY..VQ_R_USED_CURR] and *used_curr (int64, may be NULL)
+ * are written by the last block.  mu and threshold are the Python floats of the reference (the kernel
+ * rounds mu and (1 - mu) to FP32 separately, as `mu * t + (1. - mu) * s` does).  laplace_eps = 0 reproduces the reference (it has no smoothing);
+ * a positive value applies k_elem <- (k_elem + eps) / (n + K eps) * n before the division. */
+int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old, float* k, float* k_sum, float* k_elem,
+                    int k_bins, int emb_width, double mu, double threshold, double laplace_eps,
+                    double* scalars, float* results, int64_t* used_curr, void* stream);
+
+/* Gather K rows of the flattened [N*T, D] view of an NCT tensor: out[j,:] = x[n_j, :, t_j] with
+ * row = n*T + t.  Used for the restart rows y[randperm][:K] (bottleneck.py:40,70) so that only K rows
+ * are touched instead of a full permuted copy. */
+int vq_gather_rows(const float* x, const int64_t* rows, int64_t n_rows, int64_t n_utt, int64_t emb_width,
+                   int64_t t_frames, float* out, void* stream);
+
+/* Optional per-kernel timing of vq_assign with CUDA events recorded on the launching stream (what bench.py's
+ * roofline uses).  vq_profile_enable(1) clears the ring and starts recording the next (up to 64) calls;
+ * vq_profile_read synchronises on the last recorded event and writes the AVERAGE milliseconds per call of
+ * {codebook prepare, main assign kernel, exact fallback kernel, number of calls averaged}. */
+int vq_profile_enable(int on);
+int vq_profile_read(float* ms4);
+
+/* ---- host-buffer convenience path (what bench.py's e2e figure and a non-PyTorch caller use) ---- */
+typedef struct vq_host_ctx vq_host_ctx;
+
+/* Creates device buffers, pinned staging and two streams for encode jobs of up to max_rows frames.
+ * Returns NULL on failure (see vq_last_error). */
+vq_host_ctx* vq_host_ctx_create(int device, int64_t max_rows, int k_bins, int emb_width);
+void         vq_host_ctx_destroy(vq_host_ctx* ctx);
+/* Pinned staging buffers owned by the context (so callers can fill them without an extra copy). */
+float*       vq_host_ctx_x_staging(vq_host_ctx* ctx);      /* max_rows * D floats */
+int64_t*     vq_host_ctx_idx_staging(vq_host_ctx* ctx);    /* max_rows int64      */
+int          vq_host_ctx_set_codebook(vq_host_ctx* ctx, const float* k_host);
+/* Encode x_host [N,D,T] (any host memory; pinned is faster) into idx_host [N,T]: H2D copy, K1, D2H copy,
+ * chunked by utterance and double-buffered over two streams; returns after idx_host is complete. */
+int          vq_encode_host(vq_host_ctx* ctx, const float* x_host, int64_t n_utt, int64_t t_frames,
+                            int64_t* idx_host, double* sum_min_d_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB200_H */

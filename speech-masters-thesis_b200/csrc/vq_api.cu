@@ -1,0 +1,369 @@
+// libvqb200.so -- the C ABI declared in include/vqb200.h.  Host-side launch logic only; the kernels live in
+// the k*_*.cuh headers.  Built for sm_100a only (see build.py); there is no CPU path.
+#include "vq_common.cuh"
+#include "k1_prepare.cuh"
+#include "k1_assign_simt.cuh"
+#include "k1_assign_tc.cuh"
+#include "k2_gather.cuh"
+#include "k3_ema.cuh"
+
+#include <algorithm>
+#include <new>
+
+using namespace vq;
+
+static int check_shape(int64_t N, int64_t D, int64_t T, int K) {
+    VQ_REQUIRE(N >= 0 && T >= 0, "negative batch or length");
+    VQ_REQUIRE(D > 0 && D <= 65536, "emb_width out of range");
+    VQ_REQUIRE(K > 0, "k_bins must be positive");
+    VQ_REQUIRE(N * T < (int64_t(1) << 31), "more than 2^31 frames in one call");
+    return 0;
+}
+
+static int gather_smem_bytes(int D, int& Ds) {
+    Ds = (D % 2 == 0) ? D + 1 : D;
+    return int(size_t(G_TT) * Ds * 4 + G_TT * 8);
+}
+
+template <int MODE>
+static int launch_gather(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,
+                         const float* grad_commit, int64_t N, int D, int64_t T, int K, float* out, double* scalars,
+                         float* results, cudaStream_t stream) {
+    int Ds;
+    int smem = gather_smem_bytes(D, Ds);
+    VQ_REQUIRE(smem <= 200 * 1024, "emb_width too large for the gather tile (max ~780)");
+    static bool configured = false;
+    if (!configured) {
+        VQ_CUDA_OK(cudaFuncSetAttribute(gather_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    int64_t tiles = N * ((T + G_TT - 1) / G_TT);
+    int per_sm = std::max(1, std::min(8, (220 * 1024) / (smem + 1024)));
+    int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * per_sm));
+    gather_kernel<MODE><<<grid, G_THREADS, smem, stream>>>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, Ds, out,
+                                                           scalars, results, (unsigned int)grid);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- optional per-kernel event timing of vq_assign (bench.py roofline)
+namespace {
+constexpr int PROF_RING = 64;
+struct Profiler {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[PROF_RING][4];
+    bool created = false;
+} g_prof;
+inline void prof_mark(int slot, int which, cudaStream_t s) {
+    if (g_prof.on && slot >= 0) cudaEventRecord(g_prof.ev[slot][which], s);
+}
+}  // namespace
+
+extern "C" {
+
+int vq_profile_enable(int on) {
+    if (on && !g_prof.created) {
+        for (int i = 0; i < PROF_RING; ++i)
+            for (int j = 0; j < 4; ++j) VQ_CUDA_OK(cudaEventCreate(&g_prof.ev[i][j]));
+        g_prof.created = true;
+    }
+    g_prof.on = on != 0;
+    g_prof.n = 0;
+    return 0;
+}
+
+int vq_profile_read(float* ms4) {
+    VQ_REQUIRE(ms4, "null pointer");
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.f;
+    if (!g_prof.created || g_prof.n == 0) return 1;
+    const int n = g_prof.n;
+    VQ_CUDA_OK(cudaEventSynchronize(g_prof.ev[n - 1][3]));
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float ms = 0.f;
+            VQ_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[i][j], g_prof.ev[i][j + 1]));
+            ms4[j] += ms / n;
+        }
+    ms4[3] = float(n);
+    return 0;
+}
+
+int vq_version(void) { return VQB200_VERSION; }
+
+const char* vq_last_error(void) { return err_buf(); }
+
+int vq_device_supported(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_width) {
+    if (n_utt < 0 || t_frames < 0 || k_bins <= 0 || emb_width <= 0) return 0;
+    AssignWorkspace w = carve_workspace(nullptr, n_utt * t_frames, k_bins, emb_width);
+    return w.bytes + 256;
+}
+
+int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
+              int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
+              int algo, void* stream_) {
+    if (check_shape(N, D, T, K)) return 1;
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && k && idx && workspace, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    VQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    AssignWorkspace w = carve_workspace(workspace, N * T, K, int(D));
+    VQ_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see vq_workspace_bytes)");
+
+    bool use_tc = false;
+    if (algo == VQ_ALGO_TC) {
+        const char* why = tc_unsupported_reason(x, N, int(D), T, K);
+        if (why) return fail("vq_assign: VQ_ALGO_TC requested but %s", why);
+        use_tc = true;
+    } else if (algo == VQ_ALGO_AUTO) {
+        use_tc = tc_unsupported_reason(x, N, int(D), T, K) == nullptr;
+    } else {
+        VQ_REQUIRE(algo == VQ_ALGO_SIMT, "unknown algo");
+    }
+
+    VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
+    const int pslot = (g_prof.on && g_prof.n < PROF_RING) ? g_prof.n++ : -1;
+    prof_mark(pslot, 0, stream);
+    {
+        int blocks = (w.Kp * 32 + 255) / 256;
+        codebook_prepare_kernel<<<blocks, 256, 0, stream>>>(k, K, int(D), w.Kp, w.Dp, w.ee, w.hn,
+                                                            use_tc ? w.eb : nullptr, w.hdr);
+        VQ_CUDA_OK(cudaGetLastError());
+    }
+    prof_mark(pslot, 1, stream);
+    if (use_tc) {
+        if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream)) return 1;
+        prof_mark(pslot, 2, stream);
+        // exact re-scan of the rows whose BF16 shortlist could not be proven safe (count lives on the device)
+        int grid = std::min<int64_t>(2 * num_sms(), (N * T + S_BM - 1) / S_BM);
+        assign_simt_kernel<true><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
+                                                           w.unsafe_rows, &w.hdr->unsafe_count);
+        VQ_CUDA_OK(cudaGetLastError());
+    } else {
+        int64_t tiles = N * ((T + S_BM - 1) / S_BM);
+        int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));
+        assign_simt_kernel<false><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
+                                                            nullptr, nullptr);
+        VQ_CUDA_OK(cudaGetLastError());
+        prof_mark(pslot, 2, stream);
+    }
+    prof_mark(pslot, 3, stream);
+    return 0;
+}
+
+int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,
+                     int64_t T, int K, float* x_q, double* scalars, float* results, void* stream) {
+    if (check_shape(N, D, T, K)) return 1;
+    VQ_REQUIRE(scalars && results, "scalars/results must not be null");
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && idx && k && x_q, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    return launch_gather<GM_FWD>(x, idx, mask, k, nullptr, nullptr, N, int(D), T, K, x_q, scalars, results,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int vq_gather_st_bwd(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,
+                     const float* grad_commit, const double* scalars, int64_t N, int64_t D, int64_t T, int K,
+                     float* grad_x, void* stream) {
+    if (check_shape(N, D, T, K)) return 1;
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && idx && k && grad_x && grad_commit && scalars, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    return launch_gather<GM_BWD>(x, idx, mask, k, grad_xq, grad_commit, N, int(D), T, K, grad_x,
+                                 const_cast<double*>(scalars), nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int vq_decode(const int64_t* idx, const float* k, int64_t N, int64_t D, int64_t T, int K, float* x_d, void* stream) {
+    if (check_shape(N, D, T, K)) return 1;
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(idx && k && x_d, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    return launch_gather<GM_DECODE>(nullptr, idx, nullptr, k, nullptr, nullptr, N, int(D), T, K, x_d, nullptr, nullptr,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int64_t N, int64_t D, int64_t T, int K,
+                      float* stats, void* stream_) {
+    if (check_shape(N, D, T, K)) return 1;
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && idx && stats, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t tiles = N * ((T + E_TT - 1) / E_TT);
+    const size_t smem = (size_t(E_TT) + size_t(E_DS) * (E_TT + 1) + size_t(K) * E_DS + K) * 4;
+    if (smem <= 100 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured = true;
+        }
+        const int slices = int((D + E_DS - 1) / E_DS);
+        // enough CTAs to fill the machine twice over, few enough that the slab flush stays a small fraction
+        int gx = int(std::min<int64_t>(tiles, std::max<int64_t>(1, (2 * num_sms() + slices - 1) / slices)));
+        dim3 grid(gx, slices);
+        ema_accumulate_smem_kernel<<<grid, E_THREADS, smem, stream>>>(x, idx, mask, N, int(D), T, K, stats);
+    } else {
+        int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 8));
+        ema_accumulate_global_kernel<<<grid, E_THREADS, 0, stream>>>(x, idx, mask, N, int(D), T, K, stats);
+    }
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old, float* k, float* k_sum, float* k_elem, int K, int D,
+                    double mu, double threshold, double laplace_eps, double* scalars, float* results,
+                    int64_t* used_curr, void* stream_) {
+    VQ_REQUIRE(K > 0 && D > 0, "bad codebook shape");
+    VQ_REQUIRE(stats && k_rand && k_old && k && k_sum && k_elem && scalars && results, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const float* counts = stats + size_t(K) * D;
+    int g0 = std::min(64, (K + 255) / 256);
+    ema_count_total_kernel<<<g0, 256, 0, stream>>>(counts, K, scalars);
+    VQ_CUDA_OK(cudaGetLastError());
+    int grid = std::min((K + 7) / 8, num_sms() * 8);
+    // mu and (1 - mu) are rounded to FP32 independently, like `mu * t + (1. - mu) * s` on FP32 tensors
+    ema_finalize_kernel<<<grid, 256, 0, stream>>>(stats, k_rand, k_old, k, k_sum, k_elem, K, D, float(mu), float(1.0 - mu),
+                                                  float(threshold), float(laplace_eps), scalars, results, used_curr,
+                                                  (unsigned int)grid);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int vq_gather_rows(const float* x, const int64_t* rows, int64_t n_rows, int64_t N, int64_t D, int64_t T, float* out,
+                   void* stream) {
+    if (n_rows == 0) return 0;
+    VQ_REQUIRE(x && rows && out && n_rows > 0 && n_rows < (int64_t(1) << 31), "bad arguments");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    gather_rows_kernel<<<unsigned(n_rows), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, n_rows, N, int(D), T, out);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path: H2D copy -> K1 -> D2H copy, chunked by utterance and double-buffered on two streams.
+struct vq_host_ctx {
+    int device = 0;
+    int64_t max_rows = 0;
+    int K = 0, D = 0;
+    float* d_x[2] = {nullptr, nullptr};
+    int64_t* d_idx[2] = {nullptr, nullptr};
+    void* d_ws[2] = {nullptr, nullptr};
+    double* d_scalars[2] = {nullptr, nullptr};
+    size_t ws_bytes = 0;
+    int64_t chunk_rows = 0;
+    float* d_k = nullptr;
+    float* h_x = nullptr;
+    int64_t* h_idx = nullptr;
+    double* h_scalars = nullptr;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+};
+
+void vq_host_ctx_destroy(vq_host_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 2; ++i) {
+        if (c->streams[i]) cudaStreamSynchronize(c->streams[i]);
+        cudaFree(c->d_x[i]); cudaFree(c->d_idx[i]); cudaFree(c->d_ws[i]); cudaFree(c->d_scalars[i]);
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    }
+    cudaFree(c->d_k);
+    cudaFreeHost(c->h_x); cudaFreeHost(c->h_idx); cudaFreeHost(c->h_scalars);
+    delete c;
+}
+
+vq_host_ctx* vq_host_ctx_create(int device, int64_t max_rows, int K, int D) {
+    if (max_rows <= 0 || K <= 0 || D <= 0) { fail("vq_host_ctx_create: bad arguments%s"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("vq_host_ctx_create: cudaSetDevice failed%s"); return nullptr; }
+    if (!vq_device_supported()) { fail("vq_host_ctx_create: needs compute capability 10.x (B200); no fallback exists%s"); return nullptr; }
+    vq_host_ctx* c = new (std::nothrow) vq_host_ctx();
+    if (!c) return nullptr;
+    c->device = device; c->max_rows = max_rows; c->K = K; c->D = D;
+    // each in-flight chunk holds at most half of the job (rounded up), so two buffers cover any split
+    c->chunk_rows = max_rows;
+    c->ws_bytes = vq_workspace_bytes(1, c->chunk_rows, K, D);
+    bool ok = true;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaMalloc(&c->d_x[i], size_t(c->chunk_rows) * D * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_idx[i], size_t(c->chunk_rows) * 8) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_ws[i], c->ws_bytes) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_scalars[i], VQ_NUM_SCALARS * 8) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&c->d_k, size_t(K) * D * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_x, size_t(max_rows) * D * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_idx, size_t(max_rows) * 8) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_scalars, 2 * VQ_NUM_SCALARS * 8) == cudaSuccess;
+    if (!ok) {
+        fail("vq_host_ctx_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        vq_host_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+float* vq_host_ctx_x_staging(vq_host_ctx* c) { return c ? c->h_x : nullptr; }
+int64_t* vq_host_ctx_idx_staging(vq_host_ctx* c) { return c ? c->h_idx : nullptr; }
+
+int vq_host_ctx_set_codebook(vq_host_ctx* c, const float* k_host) {
+    VQ_REQUIRE(c && k_host, "null pointer");
+    VQ_CUDA_OK(cudaSetDevice(c->device));
+    VQ_CUDA_OK(cudaMemcpy(c->d_k, k_host, size_t(c->K) * c->D * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int vq_encode_host(vq_host_ctx* c, const float* x_host, int64_t N, int64_t T, int64_t* idx_host, double* sum_min_d_host) {
+    VQ_REQUIRE(c && x_host && idx_host, "null pointer");
+    VQ_REQUIRE(N >= 0 && T >= 0 && N * T <= c->max_rows, "job larger than the context was created for");
+    VQ_CUDA_OK(cudaSetDevice(c->device));
+    if (N * T == 0) { if (sum_min_d_host) *sum_min_d_host = 0.0; return 0; }
+    // split by utterance into pieces of ~32 MB of latents so copy-in, K1 and copy-out of neighbouring pieces overlap
+    const int64_t bytes_per_utt = int64_t(c->D) * T * 4;
+    int64_t utt_per_chunk = std::max<int64_t>(1, (int64_t(32) << 20) / std::max<int64_t>(1, bytes_per_utt));
+    utt_per_chunk = std::min(utt_per_chunk, N);
+    const int64_t n_chunks = (N + utt_per_chunk - 1) / utt_per_chunk;
+    // device buffers hold one chunk each; chunk offsets inside the buffer rotate so two chunks are in flight
+    double total = 0.0;
+    cudaEvent_t done[2];
+    VQ_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    VQ_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int rc = 0;
+    for (int64_t ci = 0; ci < n_chunks && !rc; ++ci) {
+        const int b = int(ci & 1);
+        cudaStream_t s = c->streams[b];
+        const int64_t n0 = ci * utt_per_chunk, nn = std::min(utt_per_chunk, N - n0);
+        if (ci >= 2) {   // the buffer's previous job (scalars read-back included) must be finished
+            if (cudaEventSynchronize(done[b]) != cudaSuccess) { rc = fail("vq_encode_host: event sync failed%s"); break; }
+            total += c->h_scalars[b * VQ_NUM_SCALARS + VQ_S_SUM_MIN_D];
+        }
+        cudaMemcpyAsync(c->d_x[b], x_host + n0 * int64_t(c->D) * T, size_t(nn) * bytes_per_utt, cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(c->d_scalars[b], 0, VQ_NUM_SCALARS * 8, s);
+        rc = vq_assign(c->d_x[b], nn, c->D, T, c->d_k, c->K, c->d_idx[b], nullptr, c->d_scalars[b], c->d_ws[b],
+                       c->ws_bytes, VQ_ALGO_AUTO, s);
+        if (rc) break;
+        cudaMemcpyAsync(idx_host + n0 * T, c->d_idx[b], size_t(nn) * T * 8, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(c->h_scalars + b * VQ_NUM_SCALARS, c->d_scalars[b], VQ_NUM_SCALARS * 8, cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(done[b], s);
+    }
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaStreamSynchronize(c->streams[b]);
+        if (e != cudaSuccess && !rc) rc = fail("vq_encode_host: %s", cudaGetErrorString(e));
+    }
+    if (!rc) {
+        const int64_t tail = std::min<int64_t>(2, n_chunks);
+        for (int64_t j = n_chunks - tail; j < n_chunks; ++j) total += c->h_scalars[(j & 1) * VQ_NUM_SCALARS + VQ_S_SUM_MIN_D];
+    }
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    if (sum_min_d_host) *sum_min_d_host = total;
+    return rc;
+}
+
+}  // extern "C"

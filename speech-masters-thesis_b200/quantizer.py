@@ -1,0 +1,388 @@
+"""B200-native drop-in for ``models/vqvae/bottleneck.py`` of vliu15/speech-masters-thesis.
+
+Same classes, constructor arguments, attributes (``k`` buffer, ``init``, ``k_sum``, ``k_elem``, ``mu``,
+``threshold``, ``k_bins``, ``emb_width``, ``level_blocks``, ``levels``), methods and return values as the
+reference (file:line cited per method).  Underneath, every tensor op of the reference's hot path is
+replaced by calls into ``libvqb200.so`` (include/vqb200.h) through a ``torch.autograd.Function``:
+
+    K1  vq_assign          distance + argmin              (bottleneck.py:92-100,126-141)
+    K2  vq_gather_st_fwd   gather + straight-through + commit loss, NCT in / NCT out (:143-145,194-201)
+        vq_gather_st_bwd   its gradient
+    K3  vq_ema_accumulate  per-code sums / counts         (:64-68)
+        vq_ema_finalize    EMA, revival, metrics          (:78-89)
+
+PyTorch is used for device memory, streams, the CPU RNG calls that must replay the reference's
+(``randperm`` / ``randn_like``) and ``torch.distributed``.  There is no fallback path: tensors must live on
+a CUDA device of compute capability 10.x and the library must be built, otherwise a RuntimeError is raised.
+"""
+import math
+
+import torch
+import torch.distributed as distributed
+import torch.nn as nn
+
+from . import _lib, dist
+from ._lib import check, ptr
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"vqb200: {what} must be a CUDA tensor (this implementation is sm_100a-only, "
+                           "there is no CPU fallback)")
+
+
+class _Workspace:
+    """Per-device scratch for K1 (BF16 codebook image, norms, fallback worklist); grows on demand."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, device, n, t, k, d):
+        lib = _lib.load()
+        need = int(lib.vq_workspace_bytes(n, t, k, d))
+        key = (device.type, device.index)
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+            cls._cache[key] = buf
+        return buf
+
+
+# --------------------------------------------------------------------------------------- raw ops
+def assign(x, k, algo="auto", want_min_d=False, scalars=None):
+    """K1 on an NCT tensor: returns (idx [N,T] int64, min_d [N,T] fp32 or None)."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n, d, t = x.shape
+    kk = k.shape[0]
+    idx = torch.empty((n, t), dtype=torch.int64, device=x.device)
+    min_d = torch.empty((n, t), dtype=torch.float32, device=x.device) if want_min_d else None
+    if n * t == 0:
+        return idx, min_d
+    ws = _Workspace.get(x.device, n, t, kk, d)
+    with torch.cuda.device(x.device):
+        check(lib.vq_assign(ptr(x), n, d, t, ptr(k), kk, ptr(idx), ptr(min_d), ptr(scalars), ptr(ws), ws.numel(),
+                            _lib.ALGOS[algo], _stream(x)), "vq_assign")
+    return idx, min_d
+
+
+def decode_nct(idx, k):
+    """idx [N,T] int64 -> [N,D,T] fp32 (bottleneck.py:160-169)."""
+    lib = _lib.load()
+    _require_cuda(idx, "indices")
+    n, t = idx.shape
+    kk, d = k.shape
+    out = torch.empty((n, d, t), dtype=torch.float32, device=idx.device)
+    if n * t:
+        with torch.cuda.device(idx.device):
+            check(lib.vq_decode(ptr(idx), ptr(k), n, d, t, kk, ptr(out), _stream(idx)), "vq_decode")
+    return out
+
+
+def gather_rows(x, rows):
+    """out[j] = x[n_j, :, t_j] for flat row ids n*T+t."""
+    lib = _lib.load()
+    n, d, t = x.shape
+    out = torch.empty((rows.numel(), d), dtype=torch.float32, device=x.device)
+    if rows.numel():
+        with torch.cuda.device(x.device):
+            check(lib.vq_gather_rows(ptr(x), ptr(rows), rows.numel(), n, d, t, ptr(out), _stream(x)), "vq_gather_rows")
+    return out
+
+
+class _QuantizeST(torch.autograd.Function):
+    """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, k, algo):
+        lib = _lib.load()
+        n, d, t = x.shape
+        kk = k.shape[0]
+        scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
+        results = torch.zeros(_lib.NUM_RESULTS, dtype=torch.float32, device=x.device)
+        idx, _ = assign(x, k, algo, scalars=scalars)
+        x_q = torch.empty_like(x)
+        if n * t:
+            with torch.cuda.device(x.device):
+                check(lib.vq_gather_st_fwd(ptr(x), ptr(idx), ptr(mask), ptr(k), n, d, t, kk, ptr(x_q), ptr(scalars),
+                                           ptr(results), _stream(x)), "vq_gather_st_fwd")
+        else:
+            results.fill_(float("nan"))
+        ctx.save_for_backward(x, idx, mask, k, scalars)
+        ctx.mark_non_differentiable(idx, scalars, results)
+        return idx, x_q, results[_lib.R_COMMIT], scalars, results
+
+    @staticmethod
+    def backward(ctx, _g_idx, g_xq, g_commit, _g_scalars, _g_results):
+        lib = _lib.load()
+        x, idx, mask, k, scalars = ctx.saved_tensors
+        n, d, t = x.shape
+        grad_x = torch.empty_like(x)
+        if g_xq is not None:
+            g_xq = g_xq.contiguous()
+        g_commit = (torch.zeros((), dtype=torch.float32, device=x.device) if g_commit is None
+                    else g_commit.to(torch.float32).contiguous())
+        if n * t:
+            with torch.cuda.device(x.device):
+                check(lib.vq_gather_st_bwd(ptr(x), ptr(idx), ptr(mask), ptr(k), ptr(g_xq), ptr(g_commit), ptr(scalars),
+                                           n, d, t, k.shape[0], ptr(grad_x), _stream(x)), "vq_gather_st_bwd")
+        return grad_x, None, None, None
+
+
+# --------------------------------------------------------------------------------------- modules
+class BottleneckBlock(nn.Module):
+    """Drop-in for ``BottleneckBlock`` (bottleneck.py:10-201)."""
+
+    def __init__(self, k_bins: int, emb_width: int, mu: float, threshold: float, laplace_eps: float = 0.0,
+                 algo: str = "auto"):
+        super().__init__()
+        self.k_bins = k_bins
+        self.emb_width = emb_width
+        self.mu = mu
+        self.threshold = threshold
+        self.laplace_eps = laplace_eps        # 0.0 == the reference (it has no Laplace smoothing)
+        self.algo = algo
+        self.reset_k()
+
+    # ---- state (bottleneck.py:20-24)
+    def reset_k(self):
+        self.init = False
+        self.k_sum = None
+        self.k_elem = None
+        self.register_buffer("k", torch.zeros(self.k_bins, self.emb_width))
+
+    # ---- restart rows (bottleneck.py:26-33, 39-40, 69-70)
+    def _tile(self, x):
+        d, ew = x.shape
+        if d < self.k_bins:
+            n_repeats = (self.k_bins + d - 1) // d
+            std = 0.01 / math.sqrt(ew)
+            x = x.repeat(n_repeats, 1)
+            x = x + torch.randn_like(x) * std
+        return x
+
+    def _restart_rows_nct(self, x, mask):
+        """K rows of the (tiled) valid rows in random order, drawn with the reference's own RNG calls
+        (CPU ``randperm``; ``randn_like`` on x's device only when there are fewer valid rows than codes),
+        but gathering K rows instead of permuting the whole batch."""
+        n, d, t = x.shape
+        flat = mask.reshape(-1) if mask is not None else None
+        valid_pos = (torch.nonzero(flat != 0)[:, 0] if flat is not None
+                     else torch.arange(n * t, device=x.device))          # host sync (the reference has three)
+        m = valid_pos.numel()
+        if m >= self.k_bins:
+            perm = torch.randperm(m)[:self.k_bins]
+            return gather_rows(x, valid_pos[perm.to(x.device)])
+        y = self._tile(gather_rows(x, valid_pos))
+        return y[torch.randperm(y.shape[0])][:self.k_bins].contiguous()
+
+    def _set_codebook(self, k_rand):
+        if distributed.is_initialized():
+            distributed.broadcast(k_rand, 0)                             # bottleneck.py:42
+        self.init = True
+        self.k = k_rand
+        assert self.k.shape == (self.k_bins, self.emb_width)
+        self.k_sum = self.k.clone()       # the reference aliases k_sum to k (:45); we update in place, so copy
+        self.k_elem = torch.ones(self.k_bins, device=self.k.device)
+
+    def init_k(self, x):
+        """bottleneck.py:35-46; ``x`` is the [M, D] matrix of valid rows."""
+        y = self._tile(x)
+        self._set_codebook(y[torch.randperm(y.shape[0])][:self.k_bins].contiguous())
+
+    def restore_k(self, num_tokens=None, threshold=1.0):
+        """bottleneck.py:48-58."""
+        self.init = True
+        assert self.k.shape == (self.k_bins, self.emb_width)
+        self.k_sum = self.k.clone()
+        self.k_elem = torch.ones(self.k_bins, device=self.k.device)
+        if num_tokens is not None:
+            expected_usage = num_tokens / self.k_bins
+            self.k_elem.data.mul_(expected_usage)
+            self.k_sum.data.mul_(expected_usage)
+        self.threshold = threshold
+
+    # ---- EMA (bottleneck.py:60-90)
+    def _update_k_nct(self, x, x_l, mask, scalars, results, k_rand=None):
+        lib = _lib.load()
+        n, d, t = x.shape
+        kk = self.k_bins
+        with torch.no_grad():
+            if k_rand is None:
+                k_rand = self._restart_rows_nct(x, mask)
+            stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), _stream(x)),
+                      "vq_ema_accumulate")
+            # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
+            # here ONE all-reduce of the packed buffer (see dist.py)
+            k_rand = dist.allreduce_statistics(stats, k_rand, kk, d)
+            k_new = torch.empty_like(self.k)
+            used_curr = torch.empty((), dtype=torch.int64, device=x.device)
+            if self.k_sum.data_ptr() == self.k.data_ptr():
+                self.k_sum = self.k_sum.clone()
+            with torch.cuda.device(x.device):
+                check(lib.vq_ema_finalize(ptr(stats), ptr(k_rand), ptr(self.k), ptr(k_new), ptr(self.k_sum),
+                                          ptr(self.k_elem), kk, d, float(self.mu), float(self.threshold),
+                                          float(self.laplace_eps), ptr(scalars), ptr(results), ptr(used_curr),
+                                          _stream(x)), "vq_ema_finalize")
+            self.k = k_new          # rebind like the reference does (:82); autograd may still hold the old tensor
+        return dict(entropy=results[_lib.R_ENTROPY], used_curr=used_curr, usage=results[_lib.R_USAGE],
+                    dk=results[_lib.R_DK])
+
+    def update_k(self, x, x_l):
+        """bottleneck.py:60-90 with the reference's signature: ``x`` [M, D] valid rows, ``x_l`` [M] codes."""
+        _require_cuda(x, "x")
+        x_nct = x.detach().float().t().contiguous().unsqueeze(0)          # [1, D, M]
+        scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
+        results = torch.zeros(_lib.NUM_RESULTS, dtype=torch.float32, device=x.device)
+        y = self._tile(x.detach().float())
+        k_rand = y[torch.randperm(y.shape[0])][:self.k_bins].contiguous()
+        return self._update_k_nct(x_nct, x_l.reshape(1, -1).contiguous(), None, scalars, results, k_rand)
+
+    # ---- layout helpers kept for API parity (bottleneck.py:92-124); the kernels read and write NCT directly
+    @staticmethod
+    def _spread(rows):
+        """The ``prenorm`` statistic of bottleneck.py:104 (every caller discards it)."""
+        return torch.norm(rows - torch.mean(rows)) / math.sqrt(rows.numel())
+
+    def preprocess(self, x, mask):
+        rows = x.transpose(1, 2).reshape(-1, x.shape[1])
+        mcol = mask.transpose(1, 2).reshape(-1, 1)
+        keep = mcol[:, 0] != 0
+        if rows.shape[-1] not in (self.emb_width, 2 * self.emb_width):
+            raise AssertionError(f"Expected {rows.shape[-1]} to be (1 or 2) * {self.emb_width}")
+        halves = rows.split(self.emb_width, dim=-1)
+        prenorm = sum(self._spread(h[keep]) for h in halves)
+        rows = halves[0] if len(halves) == 1 else halves[0] + halves[1]
+        return rows, prenorm, mcol
+
+    def postprocess(self, x_l, x_d, x_shape, mask):
+        n, t = x_shape
+        to_nct = lambda a: a.reshape(n, t, -1).transpose(1, 2).contiguous()
+        return x_l.reshape(n, t), to_nct(x_d), to_nct(mask)
+
+    # ---- row-major entry points (bottleneck.py:126-145)
+    def quantize(self, x, mask=None):
+        """``x`` [M, D] rows -> (x_l [M] int64, fit).  ``fit`` follows the reference formula, including its
+        (NT,)x(NT,1) broadcast, which reduces to sum(min_d)/K when a mask is given and mean(min_d) otherwise."""
+        _require_cuda(x, "x")
+        x_nct = x.detach().float().t().contiguous().unsqueeze(0)
+        scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
+        idx, _ = assign(x_nct, self.k, self.algo, scalars=scalars)
+        total = scalars[_lib.S_SUM_MIN_D]
+        fit = (total / x.shape[0]) if mask is None else (total / self.k_bins)
+        return idx.view(-1), fit.float()
+
+    def dequantize(self, x_l):
+        """F.embedding(x_l, k) (bottleneck.py:143-145) for any index shape -> [..., D]."""
+        flat = x_l.reshape(1, -1).contiguous()
+        out = decode_nct(flat, self.k)                                    # [1, D, M]
+        return out[0].t().contiguous().view(*x_l.shape, self.emb_width)
+
+    # ---- NCT entry points
+    def _check_input(self, x, mask):
+        _require_cuda(x, "x")
+        if x.shape[1] == 2 * self.emb_width:                              # bottleneck.py:105-113 (unused by the configs)
+            x = x[:, :self.emb_width] + x[:, self.emb_width:]
+        assert x.shape[1] == self.emb_width, f"Expected {x.shape[1]} to be (1 or 2) * {self.emb_width}"
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if mask is not None:
+            mask = mask.to(torch.float32).contiguous()
+            assert mask.numel() == x.shape[0] * x.shape[2]
+        return x, mask
+
+    def encode(self, x, mask):
+        """bottleneck.py:147-158: [N, D, T] -> [N, T] int64 (K1 only; padded frames get an index too)."""
+        x, mask = self._check_input(x.detach(), mask)
+        idx, _ = assign(x, self.k, self.algo)
+        return idx
+
+    def decode(self, x_l):
+        """bottleneck.py:160-169: [N, T] int64 -> [N, D, T]."""
+        _require_cuda(x_l, "x_l")
+        return decode_nct(x_l.contiguous(), self.k)
+
+    def forward(self, x, mask, update_k=True):
+        """bottleneck.py:171-201 -> (x_l [N,T] int64, x_q [N,D,T], commit_loss, metrics)."""
+        x, mask = self._check_input(x, mask)
+        if update_k and not self.init:
+            with torch.no_grad():
+                self._set_codebook(self._restart_rows_nct(x.detach(), mask))      # init_k (:179-180)
+        k = self.k if self.k.dtype == torch.float32 else self.k.float()
+        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo)
+        if update_k:
+            update_metrics = self._update_k_nct(x.detach(), x_l, mask, scalars, results)
+        else:
+            update_metrics = {}
+        return x_l, x_q, commit_loss, dict(fit=results[_lib.R_FIT], **update_metrics)
+
+
+class Bottleneck(nn.Module):
+    """Drop-in for ``Bottleneck`` (bottleneck.py:204-238)."""
+
+    def __init__(self, l_bins, emb_width, mu, levels, threshold, **block_kwargs):
+        super().__init__()
+        self.levels = levels
+        self.level_blocks = nn.ModuleList()
+        for _ in range(self.levels):
+            self.level_blocks.append(BottleneckBlock(l_bins, emb_width, mu, threshold, **block_kwargs))
+
+    def encode(self, xs, x_masks=None):
+        """bottleneck.py:214-216 omits the mask and raises TypeError as shipped; here the mask is optional."""
+        if x_masks is None:
+            x_masks = [None] * len(xs)
+        return [blk.encode(x, m) for blk, x, m in zip(self.level_blocks, xs, x_masks)]
+
+    def decode(self, zs, start_level=0, end_level=None):
+        if end_level is None:
+            end_level = self.levels
+        return [blk.decode(z) for blk, z in zip(self.level_blocks[start_level:end_level], zs)]
+
+    def forward(self, xs, x_masks):
+        zs, xs_quantized, commit_losses, metrics = [], [], [], []
+        for level in range(self.levels):
+            z, x_q, commit_loss, metric = self.level_blocks[level](xs[level], x_masks[level], update_k=self.training)
+            zs.append(z)
+            if not self.training:
+                x_q = x_q.detach()
+            xs_quantized.append(x_q)
+            commit_losses.append(commit_loss)
+            if self.training:
+                metrics.append(metric)
+        return zs, xs_quantized, commit_losses, metrics
+
+
+class NoBottleneckBlock(nn.Module):
+    """Identity block used when ``use_bottleneck: false`` (bottleneck.py:241-247)."""
+
+    def forward(self, x, mask, update_k=True):
+        return x, x, 0, {}
+
+    def restore_k(self):
+        return None
+
+
+class NoBottleneck(nn.Module):
+    """Identity wrapper (bottleneck.py:250-269): passes latents through, reports zero losses and metrics."""
+    METRIC_KEYS = ("entropy", "usage", "used_curr", "pn", "dk")
+
+    def __init__(self, levels):
+        super().__init__()
+        self.levels = levels
+        self.level_blocks = nn.ModuleList(NoBottleneckBlock() for _ in range(levels))
+
+    def encode(self, xs):
+        return xs
+
+    def decode(self, zs, start_level=0, end_level=None):
+        return zs
+
+    def forward(self, xs, x_masks):
+        zero = torch.zeros((), device=xs[0].device)
+        return xs, xs, [zero] * self.levels, [dict.fromkeys(self.METRIC_KEYS, zero) for _ in range(self.levels)]
