@@ -283,7 +283,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f16 tensor-core shortlist + f32 exact rescoring/fallback", "data": "synthetic",
         "config": {"workload": "ljspeech-like corpus encode (BottleneckBlock.encode / generate_vq_dataset.py:69), K=512 D=128",
                    "k_bins": K_BINS, "emb_width": EMB, "utterances_per_step_per_gpu": UTT_PER_STEP,
                    "rows_per_step_per_gpu": rows, "valid_frames_per_step_per_gpu": valid_frames, "layout": "NCT fp32",
@@ -291,7 +291,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * d * 4, "d2h_bytes_per_step": rows * 8,
                 "ms_per_step": e2e_ms / args.steps, "api": "vq_encode_host (pinned host buffers, chunked double-buffered copies)",
                 "timer": "host wall clock around synchronous calls"},
-        "gpu_launches": args.steps * 2,
+        "gpu_launches": args.steps * 3,   # codebook_prepare + assign_tc + exact fallback per step
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu["as_shipped"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,

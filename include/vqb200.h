@@ -82,6 +82,15 @@ int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames
               int64_t* idx, float* min_d, double* scalars,
               void* workspace, size_t workspace_bytes, int algo, void* stream);
 
+/* Audit variant of vq_assign (tcgen05 path only): additionally writes, per frame, the four floats
+ * {approximate best score, bound on every other code's approximate score, exact FP32 score of the shortlisted
+ * code, rigorous FP16 error bound} into shortlist4 [N*T*4] (16-byte aligned), so tests can check that the
+ * bound really dominates the observed FP16 error and count how many frames took the exact fallback
+ * (scalars[VQ_S_UNSAFE_ROWS]). */
+int vq_assign_debug(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+                    const float* k, int k_bins, int64_t* idx, float* shortlist4, double* scalars,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* K2 forward -- replaces dequantize + commit loss + straight-through + postprocess + mask multiply
  * (bottleneck.py:143-145,194,197,118-124,201).
  *   x_q[n,d,t] = (x + (k[idx] - x)) * mask      (same two FP32 roundings as the reference expression)

@@ -33,6 +33,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
     const int64_t n_tiles = LIST ? (n_rows_list + S_BM - 1) / S_BM : N * tiles_per_utt;
     const bool vec_k = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
     double tile_sum = 0.0;
+    if (LIST && blockIdx.x == 0 && tid == 0 && scalars && n_rows_list) atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n_rows_list));
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();

@@ -1,15 +1,16 @@
-// Codebook preparation for K1: ||e||^2 (FP32), the zero-padded BF16 image the tcgen05 kernel streams
-// through shared memory, and the two norms that bound the BF16 shortlisting error.
+// Codebook preparation for K1: ||e||^2 (FP32), the zero-padded FP16 image the tcgen05 kernel streams
+// through shared memory, and the two norms that bound the FP16 shortlisting error.
 // Replaces the `torch.sum(k_w**2, dim=0)` term of bottleneck.py:131-133 (computed once per call, not per row).
 #pragma once
 #include "vq_common.cuh"
+#include <cuda_fp16.h>
 
 namespace vq {
 
 // Workspace header (device memory, first 256 bytes of the workspace).
 struct AssignHeader {
-    unsigned int e_norm_max_bits;   // max_c ||bf16(e_c)||            (float bits; non-negative => uint order == float order)
-    unsigned int e_err_max_bits;    // max_c ||e_c - bf16(e_c)||
+    unsigned int e_norm_max_bits;   // max_c ||fp16(e_c)||            (float bits; non-negative => uint order == float order)
+    unsigned int e_err_max_bits;    // max_c ||e_c - fp16(e_c)||
     int unsafe_count;               // rows queued for the exact fallback
     int pad[61];
 };
@@ -19,7 +20,7 @@ struct AssignWorkspace {
     AssignHeader* hdr;
     float* ee;            // [Kp]  ||e||^2, +inf beyond K
     float* hn;            // [Kp]  ||e||^2 / 2, huge beyond K
-    __nv_bfloat16* eb;    // [Kp][Dp] BF16 image, zero padded
+    __half* eb;           // [Kp][Dp] FP16 image, zero padded
     int* unsafe_rows;     // [N*T]
     int Kp, Dp;
     size_t bytes;
@@ -37,7 +38,7 @@ inline AssignWorkspace carve_workspace(void* base, int64_t rows, int K, int D) {
     w.hdr = reinterpret_cast<AssignHeader*>(p + off);              off += 256;
     w.ee = reinterpret_cast<float*>(p + off);                      off += align256(size_t(w.Kp) * 4);
     w.hn = reinterpret_cast<float*>(p + off);                      off += align256(size_t(w.Kp) * 4);
-    w.eb = reinterpret_cast<__nv_bfloat16*>(p + off);              off += align256(size_t(w.Kp) * w.Dp * 2);
+    w.eb = reinterpret_cast<__half*>(p + off);              off += align256(size_t(w.Kp) * w.Dp * 2);
     w.unsafe_rows = reinterpret_cast<int*>(p + off);               off += align256(size_t(rows) * 4);
     w.bytes = off;
     return w;
@@ -46,15 +47,15 @@ inline AssignWorkspace carve_workspace(void* base, int64_t rows, int K, int D) {
 // One warp per code row.
 __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __restrict__ k, int K, int D, int Kp, int Dp,
                                                               float* __restrict__ ee, float* __restrict__ hn,
-                                                              __nv_bfloat16* __restrict__ eb, AssignHeader* hdr) {
+                                                              __half* __restrict__ eb, AssignHeader* hdr) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= Kp) return;
     float s = 0.f, sb = 0.f, se = 0.f;
     for (int d = lane; d < Dp; d += 32) {
         float v = (warp < K && d < D) ? k[size_t(warp) * D + d] : 0.f;
-        __nv_bfloat16 b = __float2bfloat16_rn(v);
-        float vb = __bfloat162float(b);
+        __half b = __float2half_rn(v);
+        float vb = __half2float(b);
         if (eb) eb[size_t(warp) * Dp + d] = b;
         s = fmaf(v, v, s);
         sb = fmaf(vb, vb, sb);

@@ -106,9 +106,9 @@ size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_w
     return w.bytes + 256;
 }
 
-int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
-              int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
-              int algo, void* stream_) {
+static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
+                       int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
+                       int algo, void* stream_, float* dbg) {
     if (check_shape(N, D, T, K)) return 1;
     if (N * T == 0) return 0;
     VQ_REQUIRE(x && k && idx && workspace, "null pointer");
@@ -140,7 +140,7 @@ int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, i
     }
     prof_mark(pslot, 1, stream);
     if (use_tc) {
-        if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream)) return 1;
+        if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream, dbg)) return 1;
         prof_mark(pslot, 2, stream);
         // exact re-scan of the rows whose BF16 shortlist could not be proven safe (count lives on the device)
         int grid = std::min<int64_t>(2 * num_sms(), (N * T + S_BM - 1) / S_BM);
@@ -157,6 +157,18 @@ int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, i
     }
     prof_mark(pslot, 3, stream);
     return 0;
+}
+
+int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
+              int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
+              int algo, void* stream) {
+    return assign_impl(x, N, D, T, k, K, idx, min_d, scalars, workspace, workspace_bytes, algo, stream, nullptr);
+}
+
+int vq_assign_debug(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
+                    int64_t* idx, float* shortlist4, double* scalars, void* workspace, size_t workspace_bytes, void* stream) {
+    VQ_REQUIRE(shortlist4, "null pointer");
+    return assign_impl(x, N, D, T, k, K, idx, nullptr, scalars, workspace, workspace_bytes, VQ_ALGO_TC, stream, shortlist4);
 }
 
 int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,
