@@ -188,7 +188,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
-        rc = lib.vq_assign(xd.data_ptr(), n, d, t, kd.data_ptr(), K_BINS, idx.data_ptr(), None, scalars.data_ptr(),
+        rc = lib.vq_assign(xd.data_ptr(), n, d, t, kd.data_ptr(), K_BINS, idx.data_ptr(), None, None,
                            ws.data_ptr(), ws.numel(), 0, stream)
         if rc:
             raise RuntimeError(lib.vq_last_error().decode())
@@ -215,7 +215,13 @@ def run_b200(args):
     prof = (ctypes.c_float * 4)()
     have_prof = lib.vq_profile_read(prof) == 0
     lib.vq_profile_enable(0)
-    unsafe = float(scalars[vqb200._lib.S_UNSAFE_ROWS].item()) / max(1, args.steps + max(3, args.warmup))
+    # one untimed call with the scalar block attached: how many frames took the exact fallback
+    lib.vq_assign(xd.data_ptr(), n, d, t, kd.data_ptr(), K_BINS, idx.data_ptr(), None, scalars.data_ptr(),
+                  ws.data_ptr(), ws.numel(), 0, stream)
+    unsafe = float(scalars[vqb200._lib.S_UNSAFE_ROWS].item())
+    if args.profile_only:
+        print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "k1_ms": float(prof[1])}))
+        return 0
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
     ctx = lib.vq_host_ctx_create(local, rows, K_BINS, EMB)
@@ -311,6 +317,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile-only", action="store_true", help="device-timed loop only (for ncu captures)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_b200(args)
 

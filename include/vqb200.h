@@ -95,6 +95,8 @@ int vq_assign_debug(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_
  * (bottleneck.py:143-145,194,197,118-124,201).
  *   x_q[n,d,t] = (x + (k[idx] - x)) * mask      (same two FP32 roundings as the reference expression)
  *   scalars[VQ_S_COMMIT_SQ] += sum_{mask!=0} ||k[idx]-x||^2 ; scalars[VQ_S_MASK_SUM] += sum(mask)
+ *   scalars[VQ_S_SUM_MIN_D] += sum over ALL frames of ||k[idx]-x||^2 (the winning distance in its direct form;
+ *   so call vq_assign with scalars == NULL when this kernel follows, or the numerator is counted twice)
  *   the last block writes results[VQ_R_COMMIT] = COMMIT_SQ / (MASK_SUM * D) and
  *   results[VQ_R_FIT] = SUM_MIN_D / K.  mask may be NULL (all ones). */
 int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k,

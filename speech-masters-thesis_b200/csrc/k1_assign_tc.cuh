@@ -135,6 +135,9 @@ struct Smem {           // control block placed after the data stages
     Cand cand[2][2][TM];
 };
 
+// RESCORE = true additionally re-scores the shortlisted code in exact FP32 (needed for min_d / sum(min_d) and for
+// the audit output; it also halves the safety margin); RESCORE = false decides from the approximate scores alone.
+template <bool RESCORE>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -261,37 +264,51 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             if (t >= p.T) return;
             const bool a_wins = ca.s1 >= cc.s1;
             const int c1 = a_wins ? ca.c1 : cc.c1;
+            const float s1 = fmaxf(ca.s1, cc.s1);
             // everything that is not c1 scored at most `bound` in FP16 arithmetic
             const float bound = fmaxf(fminf(ca.s1, cc.s1), fmaxf(ca.s2, cc.s2));
-            const float* xr = p.x + (size_t(n) * p.D) * p.T + t;
-            const float* er = p.k + size_t(c1) * p.D;
-            float dot = 0.f;
-            int d = 0;
-            if (p.vec_k) {
-                for (; d < p.D; d += 4) {
-                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d));
-                    dot = fmaf(__ldg(xr + size_t(d) * p.T), e4.x, dot);
-                    dot = fmaf(__ldg(xr + size_t(d + 1) * p.T), e4.y, dot);
-                    dot = fmaf(__ldg(xr + size_t(d + 2) * p.T), e4.z, dot);
-                    dot = fmaf(__ldg(xr + size_t(d + 3) * p.T), e4.w, dot);
-                }
-            }
-            for (; d < p.D; ++d) dot = fmaf(__ldg(xr + size_t(d) * p.T), __ldg(er + d), dot);
-            const float g1 = dot - p.hn[c1];
             const float xn = sqrtf(xx);
-            const float err = sqrtf(rr) * e_norm_max + xn * e_err_max                 // FP16 rounding of x and of E
-                            + 2.4e-7f * float(p.Dp) * xn * e_norm_max                // FP32 accumulation (tensor core + re-score)
-                            + 1.6e-5f * (fabsf(bound) + fabsf(g1));                   // packed index bits, FP32 roundings of the scores
+            const float acc_err = 1.2e-7f * float(p.Dp) * xn * e_norm_max;               // FP32 accumulation of D products (2^-23 D |x||e|)
+            const float err = sqrtf(rr) * e_norm_max + xn * e_err_max + acc_err          // FP16 rounding of x and of E
+                            + 1.6e-5f * (fabsf(bound) + fabsf(s1));                       // packed index bits, FP32 roundings of the scores
             const int64_t row = int64_t(n) * p.T + t;
-            if (p.dbg) {
-                float4 dv = make_float4(fmaxf(ca.s1, cc.s1), bound, g1, err);
-                reinterpret_cast<float4*>(p.dbg)[row] = dv;
+            bool safe;
+            float dot = 0.f;
+            if (RESCORE) {
+                const float* xr = p.x + (size_t(n) * p.D) * p.T + t;
+                const float* er = p.k + size_t(c1) * p.D;
+                int d = 0;
+                if (p.vec_k) {
+                    for (; d + 16 <= p.D; d += 16) {            // 16 independent loads in flight per thread
+                        float xv[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) xv[u] = __ldg(xr + size_t(d + u) * p.T);
+#pragma unroll
+                        for (int u4 = 0; u4 < 4; ++u4) {
+                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d + 4 * u4));
+                            dot = fmaf(xv[4 * u4 + 0], e4.x, dot);
+                            dot = fmaf(xv[4 * u4 + 1], e4.y, dot);
+                            dot = fmaf(xv[4 * u4 + 2], e4.z, dot);
+                            dot = fmaf(xv[4 * u4 + 3], e4.w, dot);
+                        }
+                    }
+                }
+                for (; d < p.D; ++d) dot = fmaf(__ldg(xr + size_t(d) * p.T), __ldg(er + d), dot);
+                const float g1 = dot - p.hn[c1];
+                // c1 is the exact argmax if its exact score clears every other code's approximate score + its error
+                safe = g1 > bound + err + acc_err + 1.6e-5f * fabsf(g1);
+                if (p.dbg) reinterpret_cast<float4*>(p.dbg)[row] = make_float4(s1, bound, g1, err);
+            } else {
+                // both approximate scores carry at most `err`
+                safe = (s1 - bound) > 2.f * err;
             }
-            if (g1 > bound + err) {
+            if (safe) {
                 p.idx[row] = c1;
-                const float dist = ref_distance(xx, dot, p.ee[c1]);
-                if (p.min_d) p.min_d[row] = dist;
-                sum_d += double(dist);
+                if (RESCORE) {
+                    const float dist = ref_distance(xx, dot, p.ee[c1]);
+                    if (p.min_d) p.min_d[row] = dist;
+                    sum_d += double(dist);
+                }
             } else {
                 const int pos = atomicAdd(&p.hdr->unsafe_count, 1);
                 p.unsafe_rows[pos] = int(row);
@@ -468,11 +485,13 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     VQ_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
-        VQ_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     const int grid = int(std::min<int64_t>(n_tiles, num_sms()));
-    assign_tc_kernel<<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
+    if (min_d || scalars || dbg) assign_tc_kernel<true><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
+    else assign_tc_kernel<false><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

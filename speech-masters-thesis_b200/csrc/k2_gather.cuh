@@ -39,7 +39,7 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
         double msum = scalars[VQ_S_MASK_SUM];
         gscale = float(2.0 * double(*grad_commit) / (msum * double(D)));
     }
-    double sq = 0.0, msum_local = 0.0;
+    double sq = 0.0, sq_all = 0.0, msum_local = 0.0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * G_TT;
@@ -85,7 +85,7 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
                     if (MODE == GM_FWD) {
                         const float diff = __fsub_rn(e, xv);              // (x_d - x)
                         st_stream(out + o, __fmul_rn(__fadd_rn(xv, diff), m));   // (x + (x_d - x)) * mask
-                        if (valid) acc = fmaf(diff, diff, acc);
+                        acc = fmaf(diff, diff, acc);
                     } else {
                         float g = grad_xq ? __fmul_rn(ld_stream(grad_xq + o), m) : 0.f;
                         if (valid) g = fmaf(gscale, __fsub_rn(xv, e), g);
@@ -93,13 +93,16 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
                     }
                 }
             }
-            sq += double(acc);
+            sq_all += double(acc);                    // ||k[idx] - x||^2 of EVERY row: the numerator of `fit`
+            if (valid) sq += double(acc);
         }
     }
     if (MODE == GM_FWD) {
         double s1 = block_sum(sq, red);
         double s2 = block_sum(msum_local, red);
+        double s3 = block_sum(sq_all, red);
         if (tid == 0) {
+            atomicAdd(&scalars[VQ_S_SUM_MIN_D], s3);
             atomicAdd(&scalars[VQ_S_COMMIT_SQ], s1);
             atomicAdd(&scalars[VQ_S_MASK_SUM], s2);
             __threadfence();

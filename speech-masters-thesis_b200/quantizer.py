@@ -103,7 +103,7 @@ class _QuantizeST(torch.autograd.Function):
         kk = k.shape[0]
         scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
         results = torch.zeros(_lib.NUM_RESULTS, dtype=torch.float32, device=x.device)
-        idx, _ = assign(x, k, algo, scalars=scalars)
+        idx, _ = assign(x, k, algo)            # indices only; K2 accumulates the `fit` numerator
         x_q = torch.empty_like(x)
         if n * t:
             with torch.cuda.device(x.device):
