@@ -43,7 +43,8 @@ constexpr int B_RING = 6;                    // streaming ring depth
 constexpr int B_RESIDENT_MAX = 8;            // up to 8 stages (128 KB) stay resident
 constexpr int THREADS = 512;
 constexpr int ACC_COLS = 2 * TN;             // TMEM columns [0,256): two accumulator stages
-constexpr uint32_t SPIN_LIMIT = 1u << 27;    // a lost barrier traps instead of hanging the GPU
+constexpr uint32_t SPIN_LIMIT = 1u << 22;    // a lost barrier traps (after seconds) instead of hanging the GPU
+constexpr uint32_t WAIT_HINT_NS = 2000;      // let the hardware park a waiting thread instead of spinning on issue slots
 
 struct Params {
     const float* x; const float* k; const float* ee; const float* hn;
@@ -51,6 +52,7 @@ struct Params {
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     int N, D, Dp, K, Kp, T;
     int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, resident, b_stages, vec_k;
+    uint32_t pack_mask;      // 0xFFFFFFC0, passed at run time so it lives in a register and the pack is ONE LOP3
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -67,8 +69,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(WAIT_HINT_NS) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -141,7 +143,8 @@ template <bool RESCORE>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // round up to 1024 B with pointer arithmetic on the __shared__ array so every access stays an LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* xs_base = smem;                                        // XS x 16 KB
     uint8_t* bs_base = smem + XS * X_STAGE_BYTES;                   // b_stages x 16 KB (1024-aligned)
     Smem* ctl = reinterpret_cast<Smem*>(bs_base + size_t(p.b_stages) * B_STAGE_BYTES);
@@ -353,6 +356,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 8) >> 2;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
         const float NEG_INF = __int_as_float(0xff800000);
+        const uint32_t pack_mask = p.pack_mask;
         uint32_t qa = 0, it = 0;
         for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
             float r1 = NEG_INF, r2 = NEG_INF;
@@ -380,7 +384,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         const int j = j4 * 4 + jj;
                         const float acc = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
                         const float sc = acc - hh[jj];
-                        const float pk = __uint_as_float((__float_as_uint(sc) & 0xFFFFFFC0u) | uint32_t(j));
+                        uint32_t pkb;                                   // (score & ~63) | j : the code's column rides in the low mantissa bits
+                        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(pkb) : "r"(__float_as_uint(sc)), "r"(pack_mask), "r"(uint32_t(j)));
+                        const float pk = __uint_as_float(pkb);
                         const float lo = fminf(t1, pk);
                         t1 = fmaxf(t1, pk);
                         t2 = fmaxf(t2, lo);
@@ -458,6 +464,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     p.a_bufs = w.Dp <= 256 ? 2 : 1;
     p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
     p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
+    p.pack_mask = 0xFFFFFFC0u;
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
 
     CUtensorMap x_map, b_map;
