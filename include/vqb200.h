@@ -86,10 +86,13 @@ int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames
  * {approximate best score, bound on every other code's approximate score, exact FP32 score of the shortlisted
  * code, rigorous FP16 error bound} into shortlist4 [N*T*4] (16-byte aligned), so tests can check that the
  * bound really dominates the observed FP16 error and count how many frames took the exact fallback
- * (scalars[VQ_S_UNSAFE_ROWS]). */
+ * (scalars[VQ_S_UNSAFE_ROWS]).  trace (may be NULL) receives a clock64 timeline of the first thread block,
+ * [10 events][trace_tiles], used by tools/tc_timeline.py to see which pipeline stage a tile waits on;
+ * with shortlist4 == NULL and trace != NULL the production (non-rescoring) kernel variant is traced. */
 int vq_assign_debug(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames,
                     const float* k, int k_bins, int64_t* idx, float* shortlist4, double* scalars,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    void* workspace, size_t workspace_bytes, void* stream,
+                    int64_t* trace, int trace_tiles);
 
 /* K2 forward -- replaces dequantize + commit loss + straight-through + postprocess + mask multiply
  * (bottleneck.py:143-145,194,197,118-124,201).

@@ -33,6 +33,9 @@ def build(force=False, verbose=False):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     flags = [f for f in FLAGS if f != "--use_fast_math=false"]
+    exp = os.environ.get("VQ_EXPERIMENT")
+    if exp:
+        flags = flags + [f"-DVQ_EXPERIMENT={int(exp)}"]
     cmd = [NVCC] + flags + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

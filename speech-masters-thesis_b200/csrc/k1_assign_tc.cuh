@@ -2,24 +2,30 @@
 // Replaces bottleneck.py:92-100 (NCT flatten, fused away), :129-134 (distance + argmin) and the numerator of :140.
 //
 // One persistent CTA per SM, 16 warps, warp-specialised:
-//   warp 0        TMA producer for x: FP32 [32 depth x 128 frames] boxes straight out of the NCT tensor
-//   warp 1        MMA issuer (one lane): tcgen05.mma kind::f16, A (frames x depth, FP16) from TMEM, B (codes x depth,
+//   warp 12       TMA producer for x: FP32 [32 depth x 128 frames] boxes straight out of the NCT tensor
+//   warp 13       MMA issuer (one lane): tcgen05.mma kind::f16, A (frames x depth, FP16) from TMEM, B (codes x depth,
 //                 FP16, 128B-swizzled K-major) from shared memory, FP32 accumulators in TMEM (2 stages x 128 columns)
-//   warp 2        TMA producer for the FP16 codebook image (resident in shared memory when it fits, else a ring)
-//   warp 3        TMEM allocator
-//   warps 4-7     front/back group: (front) FP32 smem tile -> FP16 pairs -> tcgen05.st into the TMEM A operand
-//                 (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and the
-//                 FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) for the PREVIOUS tile: exact FP32
-//                 re-scoring of the shortlisted code, the provable safety test, idx / min_d output
-//   warps 8-15    scan groups: tcgen05.ld the accumulators (thread == frame; each group takes 64 of the 128 code
-//                 columns), score s = x.e - ||e||^2/2, branch-free running (best, runner-up) with the code index packed
-//                 into the low mantissa bits (1 LOP3 + 3 FMNMX per code)
+//   warp 14       TMA producer for the FP16 codebook image (resident in shared memory when it fits, else a ring)
+//   warp 15       TMEM allocator
+//   warps 0-3     front/back group: (front) FP32 smem tile -> FP16 pairs -> tcgen05.st into one of up to four TMEM
+//                 A buffers (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and
+//                 the FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) a few tiles later: merge the two
+//                 scan groups' candidates, run the provable safety test, write idx (optionally re-score in FP32)
+//   warps 4-11    scan groups: tcgen05.ld the accumulators (thread == frame; each group takes 64 of the 128 code
+//                 columns) and keep a branch-free running (best, runner-up) over integer keys
 //
-// Exactness: FP16 operands only SHORTLIST.  A frame keeps the shortlisted code c1 iff its exact FP32 score beats the
-// runner-up's approximate score by more than a rigorous bound on the FP16 error,
-//     g1 > s2 + ||x - x16|| max||e16|| + ||x|| max||e - e16|| + slack,
-// which proves c1 is the exact-arithmetic argmax; otherwise the frame goes to a worklist that the exact FP32 kernel
-// (k1_assign_simt.cuh, LIST mode) re-scans.  So the output never depends on reduced-precision arithmetic.
+// Keys.  The score of code c for frame r is s = x.e_c - ||e_c||^2/2 (argmax s == argmin distance).  The scan computes
+// t = acc - (||e_c||^2/2 - B) with B = 1.5 * 2^E, E chosen per launch so that every in-range score lands in
+// [2^E, 2^(E+1)): all t share one exponent, so their bit patterns order like the scores and
+// key = (bits(t) << 6) | column is ONE integer multiply-add on the FMA pipe (no mask, no precision loss); best and
+// runner-up then cost 5 integer min/max (2.5 per code) on the ALU pipe.  Frames whose norm would leave the range are
+// sent to the exact fallback.
+//
+// Exactness: FP16 operands only SHORTLIST.  A frame keeps the shortlisted code iff the best key beats the runner-up by
+// more than twice a rigorous bound on the FP16 error,
+//     s1 - s2 > 2 (||x - x16|| max||e16|| + ||x|| max||e - e16|| + slack),
+// which proves it is the exact-arithmetic argmax; every other frame goes to a worklist that the exact FP32 kernel
+// (k1_assign_simt.cuh, LIST mode) re-scans.  The output therefore never depends on reduced-precision arithmetic.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -28,6 +34,10 @@
 
 #include "k1_prepare.cuh"
 #include "vq_common.cuh"
+
+#ifndef VQ_EXPERIMENT
+#define VQ_EXPERIMENT 0      // timing experiments (tools/experiment.sh); results are wrong by construction when != 0
+#endif
 
 namespace vq {
 namespace tc {
@@ -42,17 +52,25 @@ constexpr int B_STAGE_BYTES = TN * BKB * 2;  // 16 KB
 constexpr int B_RING = 6;                    // streaming ring depth
 constexpr int B_RESIDENT_MAX = 8;            // up to 8 stages (128 KB) stay resident
 constexpr int THREADS = 512;
+// Warp roles.  The scheduler favours the highest warp id of a sub-partition, so the single-lane issuers (TMA, MMA) sit
+// on top: as warp 1 the MMA issuer needed ~190 cycles per tcgen05.mma behind the scan warps (tools/tc_timeline.py).
+constexpr int W_XPROD = 12, W_MMA = 13, W_BPROD = 14, W_ALLOC = 15;   // warps 0-3 front/back group, 4-11 scan groups
 constexpr int ACC_COLS = 2 * TN;             // TMEM columns [0,256): two accumulator stages
-constexpr uint32_t SPIN_LIMIT = 1u << 22;    // a lost barrier traps (after seconds) instead of hanging the GPU
-constexpr uint32_t WAIT_HINT_NS = 2000;      // let the hardware park a waiting thread instead of spinning on issue slots
+constexpr int A_BUFS_MAX = 4;                // TMEM columns [256,512): up to four converted tiles in flight
+constexpr int CD = 4;                        // depth of the candidate / row-statistics hand-off between scan and back stage
+constexpr uint32_t SPIN_LIMIT = 1u << 24;    // a lost barrier traps (after seconds) instead of hanging the GPU
+constexpr uint32_t WAIT_HINT_NS = 2000;
+constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared memory up to this many (padded) codes
 
 struct Params {
-    const float* x; const float* k; const float* ee; const float* hn;
+    const float* x; const float* k; const float* ee; const float* hn; const float* hn_off;
     AssignHeader* hdr; int* unsafe_rows;
     int64_t* idx; float* min_d; double* scalars; float* dbg;
+    long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
     int N, D, Dp, K, Kp, T;
-    int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, resident, b_stages, vec_k;
-    uint32_t pack_mask;      // 0xFFFFFFC0, passed at run time so it lives in a register and the pack is ONE LOP3
+    int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, lag, resident, b_stages, vec_k;
+    int hn_in_smem;
+    uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -64,6 +82,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival per WARP: every lane has finished its part (loads landed in registers, tcgen05.wait done, shared-memory
+// writes issued), __syncwarp orders those against lane 0, which arrives for all 32.  Per-thread arrivals serialise on
+// the barrier word: 2048 of them per tile cost ~4200 cycles, more than the MMAs (measured with tools/experiment.sh).
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -73,11 +98,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(WAIT_HINT_NS) : "memory");
     return ok != 0;
 }
+// SLEEP_NS > 0 backs off with nanosleep between probes (used where a few hundred ns of wake-up latency is harmless).
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    do {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
         if (++spins > SPIN_LIMIT) __trap();
-    }
+    } while (!mbar_try_wait(bar, parity));
+}
+// One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
+// asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
+// compiler wrap every tcgen05.mma / TMA in an ELECT + R2UR.BROADCAST loop, ~190 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -96,6 +133,10 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -127,14 +168,83 @@ __device__ __forceinline__ uint64_t b_desc_base(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: FP32 accumulator, FP16 A and B, both K-major, N=128, M=128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
 
-struct Cand { float s1, s2; int c1; int pad; };          // per frame, per scan group: best, runner-up, best's code
+// ------------------------------------------------------------------------------------------------ key arithmetic
+// Offset B = 1.5 * 2^E with 2^(E-1) >= 8 max||e||^2: every frame with ||x|| <= 7.4 max||e|| keeps its scores inside
+// [-2^(E-1), 2^(E-1)), i.e. t = s + B inside [2^E, 2^(E+1)).
+struct KeySpace {
+    float offset;        // B
+    float half_range;    // 2^(E-1)
+    float ulp;           // 2^(E-23): spacing of t
+    uint32_t top6;       // the six bits of bits(t) the key drops (sign + five exponent MSBs; identical for every t)
+};
+__device__ __forceinline__ KeySpace make_key_space(float e_norm_max) {
+    KeySpace ks;
+    float need = 8.f * e_norm_max * e_norm_max;
+    if (!(need >= 1.0e-30f)) need = 1.0e-30f;
+    if (!(need <= 1.0e30f)) need = 1.0e30f;               // inf / NaN codebooks: every frame fails the range test anyway
+    int e;
+    frexpf(need, &e);                                     // need = m * 2^e, m in [0.5, 1)  =>  2^e > need
+    ks.half_range = ldexpf(1.f, e);
+    ks.offset = ldexpf(1.5f, e + 1);
+    ks.ulp = ldexpf(1.f, e + 1 - 23);
+    ks.top6 = __float_as_uint(ks.offset) & 0xFC000000u;
+    return ks;
+}
+__device__ __forceinline__ float key_to_t(uint32_t key, uint32_t top6) { return __uint_as_float((key >> 6) | top6); }
 
-struct Smem {           // control block placed after the data stages
+// Best and runner-up of 64 keys.  Four independent (best, runner-up) chains over interleaved column pairs keep enough
+// independent work in flight to cover the ALU latency.  Per pair: 2 FADD + 2 IMAD (FMA pipe), 5 min/max (ALU pipe).
+template <bool HN_SMEM>
+__device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float* hn_off, uint32_t key_mul,
+                                       uint32_t& t1, uint32_t& t2) {
+    uint32_t a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
+    const float4* hn4 = reinterpret_cast<const float4*>(hn_off);
+#pragma unroll
+    for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 h = HN_SMEM ? hn4[j4] : __ldg(hn4 + j4);
+        const float hh[4] = {h.x, h.y, h.z, h.w};
+        uint32_t key[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            const float t = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) - hh[jj];
+            key[jj] = __float_as_uint(t) * key_mul + uint32_t(j);
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int g = (j4 * 2 + h2) & 3;
+            const uint32_t hi = max(key[2 * h2], key[2 * h2 + 1]), lo = min(key[2 * h2], key[2 * h2 + 1]);
+            a2[g] = __vimax3_u32(a2[g], min(a1[g], hi), lo);
+            a1[g] = max(a1[g], hi);
+        }
+    }
+    const uint32_t b1 = max(a1[0], a1[1]), b2 = __vimax3_u32(min(a1[0], a1[1]), a2[0], a2[1]);
+    const uint32_t c1 = max(a1[2], a1[3]), c2 = __vimax3_u32(min(a1[2], a1[3]), a2[2], a2[3]);
+    t1 = max(b1, c1);
+    t2 = __vimax3_u32(min(b1, c1), b2, c2);
+}
+
+// timeline probe: event e of local tile `it` of CTA 0
+#define VQ_TRACE_NT(e, it_, nt_)                                                                  \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && int(it_) >= 8 && int(it_) < 16 && p.trace_tiles >= 32 && p.n_nt == 4) \
+            p.trace[(e) * p.trace_tiles + (int(it_) - 8) * 4 + int(nt_)] = clock64();             \
+    } while (0)
+#define VQ_TRACE(e, it_)                                                                          \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && int(it_) < p.trace_tiles)                  \
+            p.trace[(e) * p.trace_tiles + int(it_)] = clock64();                                  \
+    } while (0)
+
+struct __align__(16) Cand { uint32_t k1, k2; int c1; int pad; };   // per frame, per scan group: best key, runner-up key, best's code
+
+struct __align__(16) Smem {           // control block placed after the data stages
     uint64_t x_full[XS], x_empty[XS];
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
-    uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], cand_full[2], cand_empty[2];
+    uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[2], acc_empty[2], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
-    Cand cand[2][2][TM];
+    Cand cand[CD][2][TM];
+    float2 rowstat[CD][TM];           // (||x||^2, ||x - fp16(x)||^2) of the tiles waiting for their back stage
 };
 
 // RESCORE = true additionally re-scores the shortlisted code in exact FP32 (needed for min_d / sum(min_d) and for
@@ -148,20 +258,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     uint8_t* xs_base = smem;                                        // XS x 16 KB
     uint8_t* bs_base = smem + XS * X_STAGE_BYTES;                   // b_stages x 16 KB (1024-aligned)
     Smem* ctl = reinterpret_cast<Smem*>(bs_base + size_t(p.b_stages) * B_STAGE_BYTES);
+    float* hn_s = reinterpret_cast<float*>(ctl + 1);                // [Kp] when hn_in_smem
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float e_norm_max = __uint_as_float(p.hdr->e_norm_max_bits);
+    const KeySpace ks = make_key_space(e_norm_max);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 128); }
+        for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&ctl->a_full[i]), 128);   mbar_init(smem_u32(&ctl->a_empty[i]), 1);
-            mbar_init(smem_u32(&ctl->acc_full[i]), 1);   mbar_init(smem_u32(&ctl->acc_empty[i]), 256);
-            mbar_init(smem_u32(&ctl->cand_full[i]), 256); mbar_init(smem_u32(&ctl->cand_empty[i]), 128);
-        }
+        for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 8); }
+        for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 3) {
+    if (p.hn_in_smem) {
+        // t = acc - (||e||^2/2 - B);  padded codes (acc == 0) get t = 2^E, the smallest key of the range
+        for (int i = threadIdx.x; i < p.Kp; i += THREADS) hn_s[i] = i < p.K ? p.hn[i] - ks.offset : -2.f * ks.half_range;
+    }
+    if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -173,162 +288,213 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 
     const int first = blockIdx.x, step = gridDim.x;
 
-    if (warp == 0) {
+    if (warp == W_XPROD) {
         // ============================================================ x producer
-        if (lane == 0) {
-            uint32_t q = 0;
-            for (int tile = first; tile < p.n_tiles; tile += step) {
-                const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TM;
-                for (int ch = 0; ch < p.n_xch; ++ch, ++q) {
-                    const uint32_t s = q % XS, ph = (q / XS) & 1;
-                    mbar_wait(smem_u32(&ctl->x_empty[s]), ph ^ 1);
+        const bool leader = elect_one();
+        uint32_t q = 0;
+        for (int tile = first; tile < p.n_tiles; tile += step) {
+            const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TM;
+            for (int ch = 0; ch < p.n_xch; ++ch, ++q) {
+                const uint32_t s = q % XS, ph = (q / XS) & 1;
+                mbar_wait<100>(smem_u32(&ctl->x_empty[s]), ph ^ 1);
+                if (ch == 0) VQ_TRACE(0, q / p.n_xch);
+                if (leader) {
+#if VQ_EXPERIMENT & 32                    /* timing experiment: no x loads */
+                    mbar_arrive(smem_u32(&ctl->x_full[s]));
+#else
                     mbar_expect_tx(smem_u32(&ctl->x_full[s]), X_STAGE_BYTES);
                     tma_load_3d(smem_u32(xs_base + s * X_STAGE_BYTES), &x_map, smem_u32(&ctl->x_full[s]), t0, ch * XCH, n);
+#endif
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == W_BPROD) {
         // ============================================================ codebook producer
-        if (lane == 0) {
-            if (p.resident) {
-                for (int nt = 0; nt < p.n_nt; ++nt)
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
-                        const int s = nt * p.n_kb + kb;
+        const bool leader = elect_one();
+        if (p.resident) {
+            for (int nt = 0; nt < p.n_nt; ++nt)
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const int s = nt * p.n_kb + kb;
+                    if (leader) {
                         mbar_expect_tx(smem_u32(&ctl->b_full[s]), B_STAGE_BYTES);
                         tma_load_2d(smem_u32(bs_base + size_t(s) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, nt * TN);
                     }
-            } else {
-                uint32_t q = 0;
-                for (int tile = first; tile < p.n_tiles; tile += step)
-                    for (int nt = 0; nt < p.n_nt; ++nt)
-                        for (int kb = 0; kb < p.n_kb; ++kb, ++q) {
-                            const uint32_t s = q % p.b_stages, ph = (q / p.b_stages) & 1;
-                            mbar_wait(smem_u32(&ctl->b_empty[s]), ph ^ 1);
+                }
+        } else {
+            uint32_t q = 0;
+            for (int tile = first; tile < p.n_tiles; tile += step)
+                for (int nt = 0; nt < p.n_nt; ++nt)
+                    for (int kb = 0; kb < p.n_kb; ++kb, ++q) {
+                        const uint32_t s = q % p.b_stages, ph = (q / p.b_stages) & 1;
+                        mbar_wait<100>(smem_u32(&ctl->b_empty[s]), ph ^ 1);
+                        if (leader) {
                             mbar_expect_tx(smem_u32(&ctl->b_full[s]), B_STAGE_BYTES);
                             tma_load_2d(smem_u32(bs_base + size_t(s) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, nt * TN);
                         }
-            }
+                    }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             uint32_t qa = 0, qb = 0, it = 0;
             for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
                 const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
-                mbar_wait(smem_u32(&ctl->a_full[a]), aph);
+                mbar_wait<0>(smem_u32(&ctl->a_full[a]), aph);
                 tc_fence_after();
+                VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
                 for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
                     const uint32_t s = qa & 1, sph = (qa >> 1) & 1;
-                    mbar_wait(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
+                    mbar_wait<0>(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
                     tc_fence_after();
+                    VQ_TRACE_NT(10, it, nt);
                     const uint32_t d_tmem = tmem + s * TN;
                     for (int kb = 0; kb < p.n_kb; ++kb) {
                         uint32_t bs;
                         if (p.resident) {
                             bs = nt * p.n_kb + kb;
-                            if (it == 0) mbar_wait(smem_u32(&ctl->b_full[bs]), 0);
+                            if (it == 0) mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
                         } else {
                             bs = qb % p.b_stages;
-                            mbar_wait(smem_u32(&ctl->b_full[bs]), (qb / p.b_stages) & 1);
+                            mbar_wait<0>(smem_u32(&ctl->b_full[bs]), (qb / p.b_stages) & 1);
                         }
                         tc_fence_after();
                         const uint64_t bd = b_desc_base(smem_u32(bs_base + size_t(bs) * B_STAGE_BYTES));
 #pragma unroll
                         for (int k4 = 0; k4 < BKB / 16; ++k4) {
                             // A: 16 fp16 along depth = 8 TMEM columns; B: +32 bytes inside the swizzle row
+                            if (leader) {
+#if VQ_EXPERIMENT & 128                   /* timing experiment: A from shared memory (garbage operand) */
+                            tc_mma_ss(d_tmem, b_desc_base(smem_u32(xs_base)) + uint64_t(k4 * 2), bd + uint64_t(k4 * 2), IDESC,
+                                      (kb | k4) != 0 ? 1u : 0u);
+#elif VQ_EXPERIMENT & 64                  /* timing experiment: N = 64 per instruction */
+                            tc_mma_ts(d_tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), bd + uint64_t(k4 * 2),
+                                      (IDESC & ~(0x3Fu << 17)) | (uint32_t(64 >> 3) << 17), (kb | k4) != 0 ? 1u : 0u);
+#elif !(VQ_EXPERIMENT & 16)               /* (bit 16: timing experiment without MMAs) */
                             tc_mma_ts(d_tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), bd + uint64_t(k4 * 2), IDESC,
                                       (kb | k4) != 0 ? 1u : 0u);
+#endif
+                            }
                         }
-                        if (!p.resident) { tc_commit(smem_u32(&ctl->b_empty[bs])); ++qb; }
+                        if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[bs])); ++qb; }
                     }
-                    tc_commit(smem_u32(&ctl->acc_full[s]));
+                    if (leader) tc_commit(smem_u32(&ctl->acc_full[s]));
+                    VQ_TRACE_NT(11, it, nt);
                 }
-                tc_commit(smem_u32(&ctl->a_empty[a]));
+                if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
+                VQ_TRACE(2, it);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp < 4) {
         // ============================================================ front/back group (thread == frame)
         const int wq = warp & 3, r = wq * 32 + lane;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
-        const float e_norm_max = __uint_as_float(p.hdr->e_norm_max_bits);
         const float e_err_max = __uint_as_float(p.hdr->e_err_max_bits);
         uint32_t qx = 0, it = 0;
-        float prev_xx = 0.f, prev_rr = 0.f;
-        int prev_tile = -1;
         double sum_d = 0.0;
 
-        auto rescore = [&](int tile, uint32_t itp, float xx, float rr) {
-            const uint32_t cb = itp & 1, cph = (itp >> 1) & 1;
-            mbar_wait(smem_u32(&ctl->cand_full[cb]), cph);
+        // back stage of local tile j: merge the two scan groups, decide, write
+        auto finish = [&](uint32_t j) {
+            const int tile = first + int(j) * step;
+            const uint32_t cb = j % CD, cph = (j / CD) & 1;
+            if (wq == 0) VQ_TRACE(6, j);
+            mbar_wait<200>(smem_u32(&ctl->cand_full[cb]), cph);
+            if (wq == 0) VQ_TRACE(7, j);
             const Cand ca = ctl->cand[cb][0][r], cc = ctl->cand[cb][1][r];
-            mbar_arrive(smem_u32(&ctl->cand_empty[cb]));
+            const float2 st = ctl->rowstat[cb][r];
+            mbar_arrive_warp(smem_u32(&ctl->cand_empty[cb]));
             const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TM + r;
-            if (t >= p.T) return;
-            const bool a_wins = ca.s1 >= cc.s1;
-            const int c1 = a_wins ? ca.c1 : cc.c1;
-            const float s1 = fmaxf(ca.s1, cc.s1);
-            // everything that is not c1 scored at most `bound` in FP16 arithmetic
-            const float bound = fmaxf(fminf(ca.s1, cc.s1), fmaxf(ca.s2, cc.s2));
-            const float xn = sqrtf(xx);
-            const float acc_err = 1.2e-7f * float(p.Dp) * xn * e_norm_max;               // FP32 accumulation of D products (2^-23 D |x||e|)
-            const float err = sqrtf(rr) * e_norm_max + xn * e_err_max + acc_err          // FP16 rounding of x and of E
-                            + 1.6e-5f * (fabsf(bound) + fabsf(s1));                       // packed index bits, FP32 roundings of the scores
+            const bool in_tile = t < p.T;
+            bool unsafe = false;
             const int64_t row = int64_t(n) * p.T + t;
-            bool safe;
-            float dot = 0.f;
-            if (RESCORE) {
-                const float* xr = p.x + (size_t(n) * p.D) * p.T + t;
-                const float* er = p.k + size_t(c1) * p.D;
-                int d = 0;
-                if (p.vec_k) {
-                    for (; d + 16 <= p.D; d += 16) {            // 16 independent loads in flight per thread
-                        float xv[16];
+            if (in_tile) {
+                const float xx = st.x, rr = st.y;
+                const bool a_wins = ca.k1 >= cc.k1;
+                const int c1 = a_wins ? ca.c1 : cc.c1;
+                const uint32_t kbest = max(ca.k1, cc.k1);
+                // every code other than c1 has a key <= kbound
+                const uint32_t kbound = __vimax3_u32(min(ca.k1, cc.k1), ca.k2, cc.k2);
+                const float t_best = key_to_t(kbest, ks.top6), t_bound = key_to_t(kbound, ks.top6);
+                const float xn = sqrtf(xx);
+                const float acc_err = 1.2e-7f * float(p.Dp) * xn * e_norm_max;              // FP32 accumulation of D products
+                const float err = sqrtf(rr) * e_norm_max + xn * e_err_max + acc_err + 4.f * ks.ulp;   // FP16 rounding of x and E, roundings of t
+                // the key order is only meaningful while every score of this frame stays inside the key range
+                const bool in_range = (xn * e_norm_max + 0.51f * e_norm_max * e_norm_max) < 0.98f * ks.half_range;
+                bool safe;
+                float dot = 0.f;
+                if (RESCORE) {
+                    const int cs = min(c1, p.K - 1);
+                    const float* xr = p.x + (size_t(n) * p.D) * p.T + t;
+                    const float* er = p.k + size_t(cs) * p.D;
+                    int d = 0;
+                    if (p.vec_k) {
+                        for (; d + 16 <= p.D; d += 16) {            // 16 independent loads in flight per thread
+                            float xv[16];
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) xv[u] = __ldg(xr + size_t(d + u) * p.T);
+                            for (int u = 0; u < 16; ++u) xv[u] = __ldg(xr + size_t(d + u) * p.T);
 #pragma unroll
-                        for (int u4 = 0; u4 < 4; ++u4) {
-                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d + 4 * u4));
-                            dot = fmaf(xv[4 * u4 + 0], e4.x, dot);
-                            dot = fmaf(xv[4 * u4 + 1], e4.y, dot);
-                            dot = fmaf(xv[4 * u4 + 2], e4.z, dot);
-                            dot = fmaf(xv[4 * u4 + 3], e4.w, dot);
+                            for (int u4 = 0; u4 < 4; ++u4) {
+                                const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d + 4 * u4));
+                                dot = fmaf(xv[4 * u4 + 0], e4.x, dot);
+                                dot = fmaf(xv[4 * u4 + 1], e4.y, dot);
+                                dot = fmaf(xv[4 * u4 + 2], e4.z, dot);
+                                dot = fmaf(xv[4 * u4 + 3], e4.w, dot);
+                            }
                         }
                     }
+                    for (; d < p.D; ++d) dot = fmaf(__ldg(xr + size_t(d) * p.T), __ldg(er + d), dot);
+                    const float g1 = dot - p.hn[cs];
+                    const float s_bound = t_bound - ks.offset;      // exact: t and B share an exponent
+                    // c1 is the exact argmax if its exact score clears every other code's approximate score + its error
+                    safe = g1 > s_bound + err + acc_err + 1.2e-7f * fabsf(g1);
+                    if (p.dbg) reinterpret_cast<float4*>(p.dbg)[row] = make_float4(t_best - ks.offset, s_bound, g1, err);
+                } else {
+                    // both approximate scores carry at most `err`; the difference of two t is exact
+                    safe = (t_best - t_bound) > 2.f * err;
                 }
-                for (; d < p.D; ++d) dot = fmaf(__ldg(xr + size_t(d) * p.T), __ldg(er + d), dot);
-                const float g1 = dot - p.hn[c1];
-                // c1 is the exact argmax if its exact score clears every other code's approximate score + its error
-                safe = g1 > bound + err + acc_err + 1.6e-5f * fabsf(g1);
-                if (p.dbg) reinterpret_cast<float4*>(p.dbg)[row] = make_float4(s1, bound, g1, err);
-            } else {
-                // both approximate scores carry at most `err`
-                safe = (s1 - bound) > 2.f * err;
+                safe = safe && in_range && c1 < p.K;
+#if VQ_EXPERIMENT & 4                     /* timing experiment: never take the fallback */
+                safe = true;
+#endif
+                if (safe) {
+                    p.idx[row] = c1;
+                    if (RESCORE) {
+                        const float dist = ref_distance(xx, dot, p.ee[c1]);
+                        if (p.min_d) p.min_d[row] = dist;
+                        sum_d += double(dist);
+                    }
+                }
+                unsafe = !safe;
             }
-            if (safe) {
-                p.idx[row] = c1;
-                if (RESCORE) {
-                    const float dist = ref_distance(xx, dot, p.ee[c1]);
-                    if (p.min_d) p.min_d[row] = dist;
-                    sum_d += double(dist);
-                }
-            } else {
-                const int pos = atomicAdd(&p.hdr->unsafe_count, 1);
-                p.unsafe_rows[pos] = int(row);
+            // one atomic per warp for the rows that go to the exact fallback
+            const uint32_t m = __ballot_sync(0xffffffffu, unsafe);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&p.hdr->unsafe_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (unsafe) p.unsafe_rows[base + __popc(m & ((1u << lane) - 1u))] = int(row);
             }
         };
 
         for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
             const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
-            mbar_wait(smem_u32(&ctl->a_empty[a]), aph ^ 1);
+            mbar_wait<100>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
             tc_fence_after();
+            if (wq == 0) VQ_TRACE(3, it);
             const uint32_t a_tmem = tmem + lane_base + a_col0 + a * a_stride;
             float xx = 0.f, rr = 0.f;
             for (int ch = 0; ch < p.n_xch; ++ch, ++qx) {
                 const uint32_t s = qx % XS, ph = (qx / XS) & 1;
-                mbar_wait(smem_u32(&ctl->x_full[s]), ph);
+                mbar_wait<0>(smem_u32(&ctl->x_full[s]), ph);
+                if (wq == 0 && ch == 0) VQ_TRACE(4, it);
                 const float* xs = reinterpret_cast<const float*>(xs_base + s * X_STAGE_BYTES) + r;
                 uint32_t pk[16];
+#if VQ_EXPERIMENT & 8                     /* timing experiment: no conversion work */
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = uint32_t(j);
+                xx += 1.f;
+#else
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float v0 = xs[(2 * j) * TM], v1 = xs[(2 * j + 1) * TM];
@@ -339,82 +505,89 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     rr = fmaf(r0, r0, rr); rr = fmaf(r1, r1, rr);
                     pk[j] = *reinterpret_cast<const uint32_t*>(&h);
                 }
-                mbar_arrive(smem_u32(&ctl->x_empty[s]));                      // the stage's data now lives in registers
+#endif
+                mbar_arrive_warp(smem_u32(&ctl->x_empty[s]));                      // the stage's data now lives in registers
                 tc_st16(a_tmem + uint32_t(ch * (XCH / 2)), pk);
             }
+            ctl->rowstat[it % CD][r] = make_float2(xx, rr);                   // read back by this same thread in finish()
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(smem_u32(&ctl->a_full[a]));
-            if (prev_tile >= 0) rescore(prev_tile, it - 1, prev_xx, prev_rr);
-            prev_tile = tile; prev_xx = xx; prev_rr = rr;
+            mbar_arrive_warp(smem_u32(&ctl->a_full[a]));
+            if (wq == 0) VQ_TRACE(5, it);
+            if (it >= uint32_t(p.lag)) finish(it - p.lag);
         }
-        if (prev_tile >= 0) rescore(prev_tile, it - 1, prev_xx, prev_rr);
+        for (uint32_t j = it > uint32_t(p.lag) ? it - p.lag : 0; j < it; ++j) finish(j);
         sum_d = warp_sum(sum_d);
         if (lane == 0 && p.scalars && sum_d != 0.0) atomicAdd(&p.scalars[VQ_S_SUM_MIN_D], sum_d);
-    } else if (warp >= 8) {
+    } else if (warp < 12) {
         // ============================================================ scan groups (thread == frame)
-        const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 8) >> 2;
+        const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 4) >> 2;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
-        const float NEG_INF = __int_as_float(0xff800000);
-        const uint32_t pack_mask = p.pack_mask;
+        const uint32_t key_mul = p.key_mul;
         uint32_t qa = 0, it = 0;
         for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
-            float r1 = NEG_INF, r2 = NEG_INF;
+            uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
                 const uint32_t s = qa & 1, sph = (qa >> 1) & 1;
                 const int cbase = nt * TN + wg * 64;
-                mbar_wait(smem_u32(&ctl->acc_full[s]), sph);
+                mbar_wait<0>(smem_u32(&ctl->acc_full[s]), sph);
                 tc_fence_after();
+                if (warp == 4 && nt == 0) VQ_TRACE(8, it);
+                if (warp == 4) VQ_TRACE_NT(12, it, nt);
                 uint32_t v0[32], v1[32];
                 const uint32_t taddr = tmem + lane_base + s * TN + wg * 64;
+#if VQ_EXPERIMENT & 2                     /* timing experiment: no TMEM reads */
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v0[j] = taddr + j; v1[j] = taddr * 3 + j; }
+#else
                 tc_ld32(taddr, v0);
                 tc_ld32(taddr + 32, v1);
                 tc_wait_ld();
+#endif
                 tc_fence_before();
-                mbar_arrive(smem_u32(&ctl->acc_empty[s]));                    // accumulators are in registers: free the stage
-                float t1 = NEG_INF, t2 = NEG_INF;
-                const float4* hn4 = reinterpret_cast<const float4*>(p.hn + cbase);
-#pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4) {
-                    const float4 h = __ldg(hn4 + j4);
-                    const float hh[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float acc = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-                        const float sc = acc - hh[jj];
-                        uint32_t pkb;                                   // (score & ~63) | j : the code's column rides in the low mantissa bits
-                        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(pkb) : "r"(__float_as_uint(sc)), "r"(pack_mask), "r"(uint32_t(j)));
-                        const float pk = __uint_as_float(pkb);
-                        const float lo = fminf(t1, pk);
-                        t1 = fmaxf(t1, pk);
-                        t2 = fmaxf(t2, lo);
-                    }
-                }
+                mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                    // accumulators are in registers: free the stage
+                if (warp == 4) VQ_TRACE_NT(13, it, nt);
+                uint32_t t1, t2;
+#if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
+                t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
+#else
+                if (p.hn_in_smem) scan64<true>(v0, v1, hn_s + cbase, key_mul, t1, t2);
+                else scan64<false>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
+#endif
+                if (warp == 4) VQ_TRACE_NT(14, it, nt);
                 // fold the tile-local pair into the running pair
                 if (t1 > r1) {
-                    r2 = fmaxf(r1, t2);
+                    r2 = max(r1, t2);
                     r1 = t1;
-                    rc1 = cbase + int(__float_as_uint(t1) & 63u);
+                    rc1 = cbase + int(t1 & 63u);
                 } else {
-                    r2 = fmaxf(r2, t1);
+                    r2 = max(r2, t1);
                 }
             }
-            const uint32_t cb = it & 1, cph = (it >> 1) & 1;
-            mbar_wait(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
-            Cand c; c.s1 = r1; c.s2 = r2; c.c1 = rc1; c.pad = 0;
+            const uint32_t cb = it % CD, cph = (it / CD) & 1;
+            mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
+            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1; c.pad = 0;
             ctl->cand[cb][wg][r] = c;
-            mbar_arrive(smem_u32(&ctl->cand_full[cb]));
+            mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
+            if (warp == 4) VQ_TRACE(9, it);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
+}
+
+// hn_off[c] = ||e_c||^2/2 - B for codebooks too large for the shared-memory copy (the offset needs max||e|| first)
+__global__ void __launch_bounds__(256) codebook_offset_kernel(const float* __restrict__ hn, float* __restrict__ hn_off, int K, int Kp,
+                                                             const AssignHeader* hdr) {
+    const KeySpace ks = make_key_space(__uint_as_float(hdr->e_norm_max_bits));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Kp; i += gridDim.x * blockDim.x)
+        hn_off[i] = i < K ? hn[i] - ks.offset : -2.f * ks.half_range;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -448,24 +621,32 @@ inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64
 }
 
 inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const float* k, int K, int64_t* idx, float* min_d,
-                            double* scalars, const AssignWorkspace& w, cudaStream_t stream, float* dbg = nullptr) {
+                            double* scalars, const AssignWorkspace& w, cudaStream_t stream, float* dbg = nullptr,
+                            long long* trace = nullptr, int trace_tiles = 0, int force_rescore = -1) {
     using namespace tc;
     EncodeTiledFn encode = encode_tiled_fn();
     VQ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is unavailable");
     Params p;
-    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows;
-    p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg;
+    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows;
+    p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.D = D; p.Dp = w.Dp; p.K = K; p.Kp = w.Kp; p.T = int(T);
     p.tiles_per_utt = int((T + TM - 1) / TM);
     const int64_t n_tiles = N * p.tiles_per_utt;
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
     p.n_tiles = int(n_tiles);
     p.n_nt = w.Kp / TN; p.n_kb = w.Dp / BKB; p.n_xch = w.Dp / XCH;
-    p.a_bufs = w.Dp <= 256 ? 2 : 1;
+    p.a_bufs = std::min(A_BUFS_MAX, 256 / (w.Dp / 2));          // converted tiles that fit TMEM columns [256,512)
+    p.lag = std::min(p.a_bufs, CD - 1);                         // the back stage trails the front stage by this many tiles
     p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
     p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
-    p.pack_mask = 0xFFFFFFC0u;
+    p.key_mul = 64u;
+    p.hn_in_smem = w.Kp <= HN_SMEM_MAX ? 1 : 0;
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
+
+    if (!p.hn_in_smem) {
+        codebook_offset_kernel<<<std::min(1024, (w.Kp + 255) / 256), 256, 0, stream>>>(w.hn, w.hn_off, K, w.Kp, w.hdr);
+        VQ_CUDA_OK(cudaGetLastError());
+    }
 
     CUtensorMap x_map, b_map;
     {
@@ -488,7 +669,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(codebook) failed with CUresult %s%lld", "", (long long)r);
     }
-    const size_t smem = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem);
+    const size_t smem = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem) +
+                        (p.hn_in_smem ? size_t(w.Kp) * 4 : 0);
     VQ_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
@@ -497,7 +679,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
         configured = true;
     }
     const int grid = int(std::min<int64_t>(n_tiles, num_sms()));
-    if (min_d || scalars || dbg) assign_tc_kernel<true><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
+    const bool rescore = force_rescore >= 0 ? force_rescore != 0 : (min_d || scalars || dbg);
+    if (rescore) assign_tc_kernel<true><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
     else assign_tc_kernel<false><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
     VQ_CUDA_OK(cudaGetLastError());
     return 0;

@@ -20,6 +20,7 @@ struct AssignWorkspace {
     AssignHeader* hdr;
     float* ee;            // [Kp]  ||e||^2, +inf beyond K
     float* hn;            // [Kp]  ||e||^2 / 2, huge beyond K
+    float* hn_off;        // [Kp]  ||e||^2 / 2 - B (key offset), written only for codebooks too large for shared memory
     __half* eb;           // [Kp][Dp] FP16 image, zero padded
     int* unsafe_rows;     // [N*T]
     int Kp, Dp;
@@ -38,6 +39,7 @@ inline AssignWorkspace carve_workspace(void* base, int64_t rows, int K, int D) {
     w.hdr = reinterpret_cast<AssignHeader*>(p + off);              off += 256;
     w.ee = reinterpret_cast<float*>(p + off);                      off += align256(size_t(w.Kp) * 4);
     w.hn = reinterpret_cast<float*>(p + off);                      off += align256(size_t(w.Kp) * 4);
+    w.hn_off = reinterpret_cast<float*>(p + off);                  off += align256(size_t(w.Kp) * 4);
     w.eb = reinterpret_cast<__half*>(p + off);              off += align256(size_t(w.Kp) * w.Dp * 2);
     w.unsafe_rows = reinterpret_cast<int*>(p + off);               off += align256(size_t(rows) * 4);
     w.bytes = off;

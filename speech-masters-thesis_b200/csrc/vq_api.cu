@@ -108,7 +108,7 @@ size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_w
 
 static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
                        int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
-                       int algo, void* stream_, float* dbg) {
+                       int algo, void* stream_, float* dbg, long long* trace = nullptr, int trace_tiles = 0) {
     if (check_shape(N, D, T, K)) return 1;
     if (N * T == 0) return 0;
     VQ_REQUIRE(x && k && idx && workspace, "null pointer");
@@ -140,7 +140,8 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
     }
     prof_mark(pslot, 1, stream);
     if (use_tc) {
-        if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream, dbg)) return 1;
+        if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream, dbg, trace, trace_tiles,
+                             trace ? (dbg != nullptr) : -1)) return 1;
         prof_mark(pslot, 2, stream);
         // exact re-scan of the rows whose BF16 shortlist could not be proven safe (count lives on the device)
         int grid = std::min<int64_t>(2 * num_sms(), (N * T + S_BM - 1) / S_BM);
@@ -166,9 +167,11 @@ int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, i
 }
 
 int vq_assign_debug(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
-                    int64_t* idx, float* shortlist4, double* scalars, void* workspace, size_t workspace_bytes, void* stream) {
-    VQ_REQUIRE(shortlist4, "null pointer");
-    return assign_impl(x, N, D, T, k, K, idx, nullptr, scalars, workspace, workspace_bytes, VQ_ALGO_TC, stream, shortlist4);
+                    int64_t* idx, float* shortlist4, double* scalars, void* workspace, size_t workspace_bytes, void* stream,
+                    int64_t* trace, int trace_tiles) {
+    VQ_REQUIRE(shortlist4 || trace, "nothing to record");
+    return assign_impl(x, N, D, T, k, K, idx, nullptr, trace && !shortlist4 ? nullptr : scalars, workspace, workspace_bytes,
+                       VQ_ALGO_TC, stream, shortlist4, reinterpret_cast<long long*>(trace), trace_tiles);
 }
 
 int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,

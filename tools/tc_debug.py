@@ -27,7 +27,7 @@ def run(n, d, t, K, clustered, seed=0):
     sc = torch.zeros(16, dtype=torch.float64, device=dev)
     ws = torch.empty(int(lib.vq_workspace_bytes(n, t, K, d)), dtype=torch.uint8, device=dev)
     rc = lib.vq_assign_debug(xd.data_ptr(), n, d, t, kd.data_ptr(), K, idx.data_ptr(), dbg.data_ptr(), sc.data_ptr(),
-                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, None, 0)
     if rc:
         return {"error": lib.vq_last_error().decode()}
     torch.cuda.synchronize()
