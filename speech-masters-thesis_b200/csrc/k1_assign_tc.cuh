@@ -55,8 +55,8 @@ constexpr int THREADS = 512;
 // Warp roles.  The scheduler favours the highest warp id of a sub-partition, so the single-lane issuers (TMA, MMA) sit
 // on top: as warp 1 the MMA issuer needed ~190 cycles per tcgen05.mma behind the scan warps (tools/tc_timeline.py).
 constexpr int W_XPROD = 12, W_MMA = 13, W_BPROD = 14, W_ALLOC = 15;   // warps 0-3 front/back group, 4-11 scan groups
-constexpr int ACC_COLS = 2 * TN;             // TMEM columns [0,256): two accumulator stages
-constexpr int A_BUFS_MAX = 4;                // TMEM columns [256,512): up to four converted tiles in flight
+constexpr int ACC_STAGES_MAX = 3;            // TMEM columns [0, acc_stages*128): accumulator stages (3 when the A operand is narrow)
+constexpr int A_BUFS_MAX = 4;                // remaining TMEM columns: up to four converted tiles in flight
 constexpr int CD = 4;                        // depth of the candidate / row-statistics hand-off between scan and back stage
 constexpr uint32_t SPIN_LIMIT = 1u << 24;    // a lost barrier traps (after seconds) instead of hanging the GPU
 constexpr uint32_t WAIT_HINT_NS = 2000;
@@ -68,7 +68,7 @@ struct Params {
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
     int N, D, Dp, K, Kp, T;
-    int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, lag, resident, b_stages, vec_k;
+    int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, acc_stages, lag, resident, b_stages, vec_k;
     int hn_in_smem;
     uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
 };
@@ -241,7 +241,7 @@ struct __align__(16) Cand { uint32_t k1, k2; int c1; int pad; };   // per frame,
 struct __align__(16) Smem {           // control block placed after the data stages
     uint64_t x_full[XS], x_empty[XS];
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
-    uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[2], acc_empty[2], cand_full[CD], cand_empty[CD];
+    uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
     Cand cand[CD][2][TM];
     float2 rowstat[CD][TM];           // (||x||^2, ||x - fp16(x)||^2) of the tiles waiting for their back stage
@@ -268,7 +268,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
         for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 8); }
+        for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 8); }
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -284,7 +284,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
-    const uint32_t a_col0 = ACC_COLS, a_stride = uint32_t(p.Dp) >> 1;   // A buffers: TMEM columns [256, 256 + a_bufs * Dp/2)
+    const uint32_t a_col0 = uint32_t(p.acc_stages) * TN, a_stride = uint32_t(p.Dp) >> 1;   // A buffers follow the accumulator stages
 
     const int first = blockIdx.x, step = gridDim.x;
 
@@ -296,7 +296,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TM;
             for (int ch = 0; ch < p.n_xch; ++ch, ++q) {
                 const uint32_t s = q % XS, ph = (q / XS) & 1;
-                mbar_wait<100>(smem_u32(&ctl->x_empty[s]), ph ^ 1);
+                mbar_wait<500>(smem_u32(&ctl->x_empty[s]), ph ^ 1);
                 if (ch == 0) VQ_TRACE(0, q / p.n_xch);
                 if (leader) {
 #if VQ_EXPERIMENT & 32                    /* timing experiment: no x loads */
@@ -340,13 +340,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             uint32_t qa = 0, qb = 0, it = 0;
             for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
                 const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
-                mbar_wait<0>(smem_u32(&ctl->a_full[a]), aph);
+                mbar_wait<64>(smem_u32(&ctl->a_full[a]), aph);
                 tc_fence_after();
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
                 for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
-                    const uint32_t s = qa & 1, sph = (qa >> 1) & 1;
-                    mbar_wait<0>(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
+                    const uint32_t s = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
+                    mbar_wait<32>(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
                     tc_fence_after();
                     VQ_TRACE_NT(10, it, nt);
                     const uint32_t d_tmem = tmem + s * TN;
@@ -399,7 +399,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const int tile = first + int(j) * step;
             const uint32_t cb = j % CD, cph = (j / CD) & 1;
             if (wq == 0) VQ_TRACE(6, j);
-            mbar_wait<200>(smem_u32(&ctl->cand_full[cb]), cph);
+            mbar_wait<500>(smem_u32(&ctl->cand_full[cb]), cph);
             if (wq == 0) VQ_TRACE(7, j);
             const Cand ca = ctl->cand[cb][0][r], cc = ctl->cand[cb][1][r];
             const float2 st = ctl->rowstat[cb][r];
@@ -479,14 +479,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 
         for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
             const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
-            mbar_wait<100>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
+            mbar_wait<500>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
             tc_fence_after();
             if (wq == 0) VQ_TRACE(3, it);
             const uint32_t a_tmem = tmem + lane_base + a_col0 + a * a_stride;
             float xx = 0.f, rr = 0.f;
             for (int ch = 0; ch < p.n_xch; ++ch, ++qx) {
                 const uint32_t s = qx % XS, ph = (qx / XS) & 1;
-                mbar_wait<0>(smem_u32(&ctl->x_full[s]), ph);
+                mbar_wait<64>(smem_u32(&ctl->x_full[s]), ph);
                 if (wq == 0 && ch == 0) VQ_TRACE(4, it);
                 const float* xs = reinterpret_cast<const float*>(xs_base + s * X_STAGE_BYTES) + r;
                 uint32_t pk[16];
@@ -529,9 +529,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
-                const uint32_t s = qa & 1, sph = (qa >> 1) & 1;
+                const uint32_t s = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
                 const int cbase = nt * TN + wg * 64;
-                mbar_wait<0>(smem_u32(&ctl->acc_full[s]), sph);
+                mbar_wait<20>(smem_u32(&ctl->acc_full[s]), sph);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4) VQ_TRACE_NT(12, it, nt);
@@ -635,7 +635,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
     p.n_tiles = int(n_tiles);
     p.n_nt = w.Kp / TN; p.n_kb = w.Dp / BKB; p.n_xch = w.Dp / XCH;
-    p.a_bufs = std::min(A_BUFS_MAX, 256 / (w.Dp / 2));          // converted tiles that fit TMEM columns [256,512)
+    p.acc_stages = 2;                                           // (3 stages with 2 A buffers measured slower than 2 stages with 4)
+    p.a_bufs = std::min(A_BUFS_MAX, (512 - p.acc_stages * TN) / (w.Dp / 2));   // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, CD - 1);                         // the back stage trails the front stage by this many tiles
     p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
     p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
