@@ -285,6 +285,54 @@ def run_b200(args):
         roofline["step_breakdown_ms"] = {"codebook_prepare": float(prof[0]), "assign_main": float(prof[1]),
                                          "exact_fallback": float(prof[2])}
 
+    # ---- the other kernels of the training path at the same batch (each timed alone, CUDA events, best of 10)
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    md = mask.to(dev)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    x_q = torch.empty_like(xd)
+    res = torch.zeros(8, device=dev)
+    stats = torch.zeros(K_BINS * EMB + K_BINS, device=dev)
+    g_commit = torch.ones((), device=dev)
+    k_sum, k_elem, k_new = kd.clone(), torch.ones(K_BINS, device=dev), torch.empty_like(kd)
+    k2_fwd = timed(lambda: lib.vq_gather_st_fwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K_BINS,
+                                                x_q.data_ptr(), scalars.data_ptr(), res.data_ptr(), stream))
+    k2_bwd = timed(lambda: lib.vq_gather_st_bwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), x_q.data_ptr(),
+                                                g_commit.data_ptr(), scalars.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
+    k2_dec = timed(lambda: lib.vq_decode(idx.data_ptr(), kd.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
+    k3_acc = timed(lambda: lib.vq_ema_accumulate(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), n, d, t, K_BINS, stats.data_ptr(), stream))
+    k3_fin = timed(lambda: lib.vq_ema_finalize(stats.data_ptr(), kd.data_ptr(), kd.data_ptr(), k_new.data_ptr(), k_sum.data_ptr(),
+                                               k_elem.data_ptr(), K_BINS, EMB, 0.99, 1.0, 0.0, scalars.data_ptr(), res.data_ptr(), None, stream))
+
+    def gbps(nbytes, ms_):
+        return nbytes / (ms_ * 1e-3) / 1e9
+
+    other = {
+        "K2_gather_st_fwd": {"ms": k2_fwd, "algorithmic_bytes": rows * (8 * EMB + 12), "GBps": gbps(rows * (8 * EMB + 12), k2_fwd)},
+        "K2_gather_st_bwd": {"ms": k2_bwd, "algorithmic_bytes": rows * (12 * EMB + 12), "GBps": gbps(rows * (12 * EMB + 12), k2_bwd)},
+        "K2_decode": {"ms": k2_dec, "algorithmic_bytes": rows * (4 * EMB + 8), "GBps": gbps(rows * (4 * EMB + 8), k2_dec)},
+        "K3_ema_accumulate": {"ms": k3_acc, "algorithmic_bytes": valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1),
+                              "GBps": gbps(valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1), k3_acc)},
+        "K3_ema_finalize": {"ms": k3_fin, "algorithmic_bytes": 4 * K_BINS * (6 * EMB + 3), "GBps": gbps(4 * K_BINS * (6 * EMB + 3), k3_fin)},
+    }
+    for v in other.values():
+        v["frac_of_hbm_peak"] = v["GBps"] / hbm_peak
+    # whole training-mode forward of the module (K1 + K2 + K3a + K3b + restart-row glue, one host sync like the reference has three)
+    blk = vqb200.BottleneckBlock(K_BINS, EMB, 0.99, 1.0).to(dev)
+    blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
+    blk.train()
+    fwd_ms = timed(lambda: blk(xd, md, update_k=True), reps=5)
+    other["module_forward_train"] = {"ms": fwd_ms, "valid_frames_per_s": valid_frames / (fwd_ms * 1e-3)}
+
     cpu, cores, sample_desc = cpu_reference_rate(budget_s=16.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -303,6 +351,7 @@ def run_b200(args):
         "cpu_baseline": {"value": cpu["as_shipped"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,
                          "without_nxn_temp": cpu["without_nxn_temp"]},
         "index_match": {"device_path": audit, "host_path": audit_host},
+        "training_path_kernels": other,
         "unsafe_rows_per_step": unsafe,
     }
     print(json.dumps(line))
