@@ -10,77 +10,163 @@ namespace vq {
 
 constexpr int E_TT = 128;        // frames per tile
 constexpr int E_DS = 32;         // depth slice owned by one CTA (lane == depth)
-constexpr int E_THREADS = 256;   // 8 warps; warp w owns the codes with (c & 7) == w
+constexpr int E_THREADS = 256;   // large-K kernel
 
-// Small-K variant: the CTA keeps a private [K][32] slab of sums in shared memory.  Lane d of warp w is the
-// ONLY thread that ever touches acc[c][d] for c & 7 == w, so the read-modify-write needs no atomics
-// ("owner computes"); rows are visited in order, the branch on the code is warp-uniform.
-__global__ void __launch_bounds__(E_THREADS)
+// ---- small-K kernel: private [K][32] slab in shared memory, "owner computes", cp.async tile pipeline
+constexpr int EA_WARPS = 16;                 // warp w owns the codes with (c & 15) == w
+constexpr int EA_THREADS = EA_WARPS * 32;
+constexpr int EA_STAGES = 4;                 // tiles in flight per CTA (the kernel is a pure HBM stream)
+constexpr int EA_XS = E_TT + 4;              // 16-byte aligned rows for 16-byte cp.async (column reads then take 4 wavefronts; they are rare)
+constexpr int EA_STAGE_BYTES = E_DS * EA_XS * 4 + E_TT * 8 + E_TT * 4;   // x slice + idx (int64) + mask
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Lane d of warp w is the ONLY thread that ever touches acc[c][d] for (c & 15) == w, so the read-modify-write needs no
+// atomics; each warp compacts the rows it owns with ballots (no per-row branch for the other 15 warps) and sums runs of
+// one code in a register before touching the slab.  Tiles stream through a 4-stage cp.async ring (16-byte copies).
+__global__ void __launch_bounds__(EA_THREADS, 1)
 ema_accumulate_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
                            int64_t N, int D, int64_t T, int K, float* __restrict__ stats) {
-    extern __shared__ __align__(16) float smem[];
-    int* s_code = reinterpret_cast<int*>(smem);         // [E_TT], -1 for masked rows (16-byte aligned: read as int4)
-    float* Xs = smem + E_TT;                            // [E_DS][E_TT + 1]
-    float* acc = Xs + E_DS * (E_TT + 1);                // [K][E_DS]
-    float* cnt = acc + size_t(K) * E_DS;                // [K]      (only used by slice 0)
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* stage0 = smem_raw;                                                    // EA_STAGES x EA_STAGE_BYTES
+    float* acc = reinterpret_cast<float*>(smem_raw + size_t(EA_STAGES) * EA_STAGE_BYTES);   // [K][E_DS]
+    float* cnt = acc + size_t(K) * E_DS;                                            // [K] (slice 0 only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slice = blockIdx.y;
     const int d0 = slice * E_DS;
     const int dn = min(E_DS, D - d0);
     const bool count_here = slice == 0;
-
-    for (int i = tid; i < K * E_DS; i += E_THREADS) acc[i] = 0.f;
-    for (int i = tid; i < K; i += E_THREADS) cnt[i] = 0.f;
-
     const int64_t tiles_per_utt = (T + E_TT - 1) / E_TT;
     const int64_t n_tiles = N * tiles_per_utt;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * E_TT;
-        const int tt = int(min(int64_t(E_TT), T - t0));
-        __syncthreads();
-        if (tid < E_TT) {
-            int c = -1;
-            if (tid < tt) {
-                float m = mask ? mask[n * T + t0 + tid] : 1.f;
-                if (m != 0.f) c = int(min(max(idx[n * T + t0 + tid], int64_t(0)), int64_t(K - 1)));
+    const bool vec16 = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+
+    for (int i = tid; i < K * E_DS; i += EA_THREADS) acc[i] = 0.f;
+    for (int i = tid; i < K; i += EA_THREADS) cnt[i] = 0.f;
+
+    auto issue = [&](int64_t tile, int st) {
+        float* Xs = reinterpret_cast<float*>(stage0 + size_t(st) * EA_STAGE_BYTES);
+        int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + E_DS * EA_XS);
+        float* s_mask = reinterpret_cast<float*>(s_idx + E_TT);
+        if (tile < n_tiles) {
+            const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * E_TT;
+            const int tt = int(min(int64_t(E_TT), T - t0));
+            if (vec16) {                          // 16 bytes per copy: 2 copies per thread per tile
+#pragma unroll
+                for (int i = tid; i < E_DS * (E_TT / 4); i += EA_THREADS) {
+                    const int d = i >> 5, t = (i & 31) * 4;
+                    float* dst = Xs + d * EA_XS + t;
+                    if (d < dn && t < tt) cp_async16(dst, x + (size_t(n) * D + d0 + d) * T + t0 + t);   // T % 4 == 0: a chunk never straddles tt
+                    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int i = tid; i < E_DS * E_TT; i += EA_THREADS) {
+                    const int d = i >> 7, t = i & (E_TT - 1);
+                    float* dst = Xs + d * EA_XS + t;
+                    if (d < dn && t < tt) cp_async4(dst, x + (size_t(n) * D + d0 + d) * T + t0 + t);
+                    else *dst = 0.f;
+                }
             }
-            s_code[tid] = c;
+            if (tid < E_TT) {
+                if (tid < tt) {
+                    cp_async8(s_idx + tid, idx + n * T + t0 + tid);
+                    if (mask) cp_async4(s_mask + tid, mask + n * T + t0 + tid);
+                    else s_mask[tid] = 1.f;
+                } else {
+                    s_idx[tid] = -1;
+                    s_mask[tid] = 0.f;
+                }
+            }
         }
-        // stage the [32 depth][128 frames] slice, coalesced along frames
-        for (int i = tid; i < E_DS * E_TT; i += E_THREADS) {
-            int d = i / E_TT, t = i % E_TT;
-            float v = 0.f;
-            if (d < dn && t < tt) v = ld_stream(x + (size_t(n) * D + d0 + d) * T + t0 + t);
-            Xs[d * (E_TT + 1) + t] = v;
+        cp_async_commit();
+    };
+
+    const int64_t first = blockIdx.x, step = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < EA_STAGES - 1; ++s) issue(first + s * step, s);
+
+    int it = 0;
+    int pc[4] = {-1, -1, -1, -1};                // pending (code, partial sum, count) of this warp's four chains
+    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pn[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t tile = first; tile < n_tiles; tile += step, ++it) {
+        cp_async_wait<EA_STAGES - 2>();          // this tile's group has landed (for this thread's copies)
+        __syncthreads();                         // ... for everyone's; and the stage freed last iteration is reusable
+        issue(tile + int64_t(EA_STAGES - 1) * step, (it + EA_STAGES - 1) % EA_STAGES);
+        const int st = it % EA_STAGES;
+        const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(st) * EA_STAGE_BYTES);
+        const int64_t* s_idx = reinterpret_cast<const int64_t*>(Xs + E_DS * EA_XS);
+        const float* s_mask = reinterpret_cast<const float*>(s_idx + E_TT);
+        const float* xcol = Xs + lane * EA_XS;
+        int code[4];
+        unsigned m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = j * 32 + lane;
+            const int64_t ci = s_idx[t];
+            code[j] = (s_mask[t] != 0.f && ci >= 0) ? int(min(ci, int64_t(K - 1))) : -1;
+            m[j] = __ballot_sync(0xffffffffu, code[j] >= 0 && (code[j] & (EA_WARPS - 1)) == warp);
         }
-        __syncthreads();
-        // owner-computes scatter: 4 rows per step so that independent read-modify-writes overlap
-        for (int t = 0; t < tt; t += 4) {
-            int4 c4 = *reinterpret_cast<const int4*>(&s_code[t]);
-            int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+        // Four independent chains (one per 32-frame group), each with its own pending (code, sum, count): the shuffles
+        // and column reads of a step are issued together, so their latency is paid once per step, not once per row.
+        while (m[0] | m[1] | m[2] | m[3]) {
+            int c[4];
+            float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int c = cs[j];
-                if (c >= 0 && (c & 7) == warp) {
-                    float* a = acc + size_t(c) * E_DS + lane;
-                    *a += Xs[lane * (E_TT + 1) + t + j];
-                    if (count_here && lane == 0) cnt[c] += 1.f;
+                c[j] = -1;
+                v[j] = 0.f;
+                if (m[j]) {                       // warp-uniform
+                    const int b = __ffs(m[j]) - 1;
+                    m[j] &= m[j] - 1;
+                    c[j] = __shfl_sync(0xffffffffu, code[j], b);
+                    v[j] = xcol[j * 32 + b];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c[j] < 0) continue;
+                if (c[j] != pc[j]) {              // runs of one code (hot codes!) collapse into a register sum
+                    if (pc[j] >= 0) {
+                        acc[size_t(pc[j]) * E_DS + lane] += ps[j];
+                        if (count_here && lane == 0) cnt[pc[j]] += pn[j];
+                    }
+                    pc[j] = c[j]; ps[j] = v[j]; pn[j] = 1.f;
+                } else {
+                    ps[j] += v[j]; pn[j] += 1.f;
                 }
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (pc[j] >= 0) {
+            acc[size_t(pc[j]) * E_DS + lane] += ps[j];
+            if (count_here && lane == 0) cnt[pc[j]] += pn[j];
+        }
+    cp_async_wait<0>();
     __syncthreads();
     // flush the private slab: one FP32 reduction per touched cell, coalesced along depth
     float* sums = stats;
     float* counts = stats + size_t(K) * D;
-    for (int i = tid; i < K * E_DS; i += E_THREADS) {
-        int c = i / E_DS, d = i % E_DS;
-        float v = acc[i];
+    for (int i = tid; i < K * E_DS; i += EA_THREADS) {
+        const int c = i / E_DS, d = i % E_DS;
+        const float v = acc[i];
         if (d < dn && v != 0.f) atomicAdd(&sums[size_t(c) * D + d0 + d], v);
     }
     if (count_here)
-        for (int c = tid; c < K; c += E_THREADS)
+        for (int c = tid; c < K; c += EA_THREADS)
             if (cnt[c] != 0.f) atomicAdd(&counts[c], cnt[c]);
 }
 

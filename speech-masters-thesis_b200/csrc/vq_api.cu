@@ -213,18 +213,18 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
     VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t tiles = N * ((T + E_TT - 1) / E_TT);
-    const size_t smem = (size_t(E_TT) + size_t(E_DS) * (E_TT + 1) + size_t(K) * E_DS + K) * 4;
-    if (smem <= 100 * 1024) {
+    const size_t smem = size_t(EA_STAGES) * EA_STAGE_BYTES + (size_t(K) * E_DS + K) * 4;
+    if (smem <= 220 * 1024) {
         static bool configured = false;
         if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             configured = true;
         }
         const int slices = int((D + E_DS - 1) / E_DS);
-        // enough CTAs to fill the machine twice over, few enough that the slab flush stays a small fraction
-        int gx = int(std::min<int64_t>(tiles, std::max<int64_t>(1, (2 * num_sms() + slices - 1) / slices)));
+        // one CTA per SM: a private slab per (row chunk, depth slice); few enough chunks that the flush stays small
+        int gx = int(std::min<int64_t>(tiles, std::max<int64_t>(1, num_sms() / slices)));
         dim3 grid(gx, slices);
-        ema_accumulate_smem_kernel<<<grid, E_THREADS, smem, stream>>>(x, idx, mask, N, int(D), T, K, stats);
+        ema_accumulate_smem_kernel<<<grid, EA_THREADS, smem, stream>>>(x, idx, mask, N, int(D), T, K, stats);
     } else {
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 8));
         ema_accumulate_global_kernel<<<grid, E_THREADS, 0, stream>>>(x, idx, mask, N, int(D), T, K, stats);
