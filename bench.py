@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -136,16 +136,20 @@ def run_reference(args):
         for x, mask, _ in batches:
             O.encode(st, x, mask, faithful_fit=True)
 
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    for _ in range(args.steps):          # each step is ~2 s of host work: stop after ~90 s so the arm ends within minutes
         step()
+        done += 1
+        if time.perf_counter() - t0 > 90.0:
+            break
     dt = time.perf_counter() - t0
-    value = frames * args.steps / dt
+    value = frames * done / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "steps_timed": done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ljspeech-like corpus encode (BottleneckBlock.encode), K=512 D=128, CPU port of the reference",
                    "k_bins": K_BINS, "emb_width": EMB, "utterances_per_step": per_step_utts, "batch_size": 8,
@@ -276,8 +280,13 @@ def run_b200(args):
     flops = 2.0 * rows * K_BINS * EMB
     achieved = flops / (k1_ms * 1e-3) / 1e12
     hbm_bytes = rows * (4 * EMB + 8) + 4 * K_BINS * EMB
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))["traffic_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src, "kernel": "K1 distance+argmin (vq_assign main kernel)",
+                "traffic": traffic, "algorithmic_flop_per_launch": flops, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src, "kernel": "K1 distance+argmin (vq_assign main kernel)",
                 "kernel_ms": k1_ms, "kernel_ms_source": "library CUDA events around the kernel" if have_prof and prof[1] > 0
                 else "whole vq_assign step (prep + main + fallback kernels)",
                 "hbm_secondary": {"achieved_GBps": hbm_bytes / (k1_ms * 1e-3) / 1e9, "peak_GBps": float(peaks.get("hbm_gbs", 6650.0))}}
@@ -363,8 +372,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile-only", action="store_true", help="device-timed loop only (for ncu captures)")
     args = ap.parse_args()
