@@ -18,6 +18,7 @@ import argparse
 import ctypes
 import json
 import os
+import signal
 import subprocess
 import sys
 import threading
@@ -168,6 +169,7 @@ def run_b200(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    signal.alarm(env_int("VQ_BENCH_TIMEOUT", 540))      # a wedged collective must not eat the GPU lease
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
@@ -247,7 +249,26 @@ def run_b200(args):
     idx_host = torch.frombuffer((ctypes.c_int64 * rows).from_address(hidx), dtype=torch.int64).clone()
     lib.vq_host_ctx_destroy(ctx)
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # whole training-mode forward of the module on every rank (K1 + K2 + K3a + ONE all-reduce + K3b + restart-row glue)
+    def timed_all(fn, reps=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        best = 1e9
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    md_all = mask.to(dev)
+    blk = vqb200.BottleneckBlock(K_BINS, EMB, 0.99, 1.0).to(dev)
+    blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
+    blk.train()
+    fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
+    del blk
+
+    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms], dtype=torch.float64, device=dev)
     frames = torch.tensor([float(valid_frames), float(rows)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, dist.ReduceOp.MAX)
@@ -256,7 +277,7 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    ms, e2e_ms = float(times[0]), float(times[1])
+    ms, e2e_ms, fwd_ms = float(times[0]), float(times[1]), float(times[2])
     tot_valid, tot_rows = float(frames[0]), float(frames[1])
     value = tot_valid * args.steps / (ms * 1e-3)
     e2e_value = tot_valid * args.steps / (e2e_ms * 1e-3)
@@ -335,12 +356,8 @@ def run_b200(args):
     }
     for v in other.values():
         v["frac_of_hbm_peak"] = v["GBps"] / hbm_peak
-    # whole training-mode forward of the module (K1 + K2 + K3a + K3b + restart-row glue, one host sync like the reference has three)
-    blk = vqb200.BottleneckBlock(K_BINS, EMB, 0.99, 1.0).to(dev)
-    blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
-    blk.train()
-    fwd_ms = timed(lambda: blk(xd, md, update_k=True), reps=5)
-    other["module_forward_train"] = {"ms": fwd_ms, "valid_frames_per_s": valid_frames / (fwd_ms * 1e-3)}
+    other["module_forward_train"] = {"ms": fwd_ms, "valid_frames_per_s": tot_valid / (fwd_ms * 1e-3),
+                                     "note": "whole nn.Module training forward per rank (K1+K2+K3a+all-reduce+K3b+restart-row glue), max over ranks"}
 
     cpu, cores, sample_desc = cpu_reference_rate(budget_s=16.0)
     line = {
