@@ -8,16 +8,9 @@
 
 namespace vq {
 
-constexpr int E_TT = 128;        // frames per tile
-constexpr int E_DS = 32;         // depth slice owned by one CTA (lane == depth)
-constexpr int E_THREADS = 256;   // large-K kernel
-
-// ---- small-K kernel: private [K][32] slab in shared memory, "owner computes", cp.async tile pipeline
-constexpr int EA_WARPS = 16;                 // warp w owns the codes with (c & 15) == w
-constexpr int EA_THREADS = EA_WARPS * 32;
-constexpr int EA_STAGES = 4;                 // tiles in flight per CTA (the kernel is a pure HBM stream)
-constexpr int EA_XS = E_TT + 4;              // 16-byte aligned rows for 16-byte cp.async (column reads then take 4 wavefronts; they are rare)
-constexpr int EA_STAGE_BYTES = E_DS * EA_XS * 4 + E_TT * 8 + E_TT * 4;   // x slice + idx (int64) + mask
+constexpr int E_TT = 128;        // frames per tile      (fallback kernel for emb_width > 128)
+constexpr int E_DS = 32;         // depth slice staged at a time
+constexpr int E_THREADS = 256;
 
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
@@ -32,142 +25,210 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Lane d of warp w is the ONLY thread that ever touches acc[c][d] for (c & 15) == w, so the read-modify-write needs no
-// atomics; each warp compacts the rows it owns with ballots (no per-row branch for the other 15 warps) and sums runs of
-// one code in a register before touching the slab.  Tiles stream through a 4-stage cp.async ring (16-byte copies).
-__global__ void __launch_bounds__(EA_THREADS, 1)
-ema_accumulate_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
-                           int64_t N, int D, int64_t T, int K, float* __restrict__ stats) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* stage0 = smem_raw;                                                    // EA_STAGES x EA_STAGE_BYTES
-    float* acc = reinterpret_cast<float*>(smem_raw + size_t(EA_STAGES) * EA_STAGE_BYTES);   // [K][E_DS]
-    float* cnt = acc + size_t(K) * E_DS;                                            // [K] (slice 0 only)
+// ---- sorted-run kernels.  Tiles of 64 frames x (up to 64 or 128) depths stream through a cp.async ring; one warp
+// bitonic-sorts the NEXT tile's (code, frame) keys while the other 15 walk the current tile's rows in code order.  A run of
+// equal codes is summed in registers (lane == depth) by the warp in whose row range it STARTS, so no two warps ever touch
+// the same code in one tile:
+//   SLAB = true  (K*64*4 B fits shared memory, e.g. K <= 512): the CTA owns a 64-deep depth slice and a private [K][64]
+//                slab; a run is one non-atomic read-modify-write of the slab; the slab is flushed once per CTA.
+//   SLAB = false (any K, D <= 128): a run is one coalesced FP32 reduction per 32-depth group straight to L2.
+// Either way a row costs ~15 issued instructions (the first version spent ~80 per row and depth slice) and a hot code
+// costs one update per tile instead of one per row.
+constexpr int ER_TT = 64;                    // frames per tile
+constexpr int ER_XS = ER_TT + 4;             // row stride (16-byte aligned rows)
+constexpr int ER_WARPS = 16;                 // warp 15 sorts, warps 0..14 accumulate
+constexpr int ER_THREADS = ER_WARPS * 32;
+constexpr int ER_PER = (ER_TT + ER_WARPS - 2) / (ER_WARPS - 1);   // sorted rows per accumulating warp (5)
 
+template <bool SLAB> struct ErCfg;
+template <> struct ErCfg<true>  { static constexpr int DW = 64,  STAGES = 5; };   // depth slice width, ring depth
+template <> struct ErCfg<false> { static constexpr int DW = 128, STAGES = 6; };
+template <bool SLAB> constexpr int er_stage_bytes() { return ErCfg<SLAB>::DW * ER_XS * 4 + ER_TT * 8 + ER_TT * 4; }
+template <bool SLAB> inline size_t er_smem_bytes(int K) {
+    return size_t(ErCfg<SLAB>::STAGES) * er_stage_bytes<SLAB>() + 2 * ER_TT * 4 + (SLAB ? (size_t(K) * ErCfg<true>::DW + K) * 4 : 0);
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(ER_THREADS, 1)
+ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
+                           int64_t N, int D, int64_t T, int K, float* __restrict__ stats) {
+    constexpr int DW = ErCfg<SLAB>::DW, STAGES = ErCfg<SLAB>::STAGES, NQ = DW / 32, STAGE_BYTES = er_stage_bytes<SLAB>();
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* stage0 = smem_raw;
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw + size_t(STAGES) * STAGE_BYTES);   // [2][ER_TT] keys, ~0u = no row
+    float* slab = reinterpret_cast<float*>(sorted + 2 * ER_TT);                               // [K][DW]   (SLAB only)
+    float* scnt = slab + size_t(K) * DW;                                                       // [K]       (SLAB, slice 0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slice = blockIdx.y;
-    const int d0 = slice * E_DS;
-    const int dn = min(E_DS, D - d0);
-    const bool count_here = slice == 0;
-    const int64_t tiles_per_utt = (T + E_TT - 1) / E_TT;
+    const int d0 = SLAB ? blockIdx.y * DW : 0;
+    const int dn = min(DW, D - d0);
+    const bool count_here = !SLAB || blockIdx.y == 0;
+    const int tiles_per_utt = int((T + ER_TT - 1) / ER_TT);
     const int64_t n_tiles = N * tiles_per_utt;
     const bool vec16 = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    float* sums = stats;
+    float* counts = stats + size_t(K) * D;
 
-    for (int i = tid; i < K * E_DS; i += EA_THREADS) acc[i] = 0.f;
-    for (int i = tid; i < K; i += EA_THREADS) cnt[i] = 0.f;
+    if (SLAB) {
+        for (int i = tid; i < K * DW; i += ER_THREADS) slab[i] = 0.f;
+        for (int i = tid; i < K; i += ER_THREADS) scnt[i] = 0.f;
+    }
 
-    auto issue = [&](int64_t tile, int st) {
-        float* Xs = reinterpret_cast<float*>(stage0 + size_t(st) * EA_STAGE_BYTES);
-        int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + E_DS * EA_XS);
-        float* s_mask = reinterpret_cast<float*>(s_idx + E_TT);
-        if (tile < n_tiles) {
-            const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * E_TT;
-            const int tt = int(min(int64_t(E_TT), T - t0));
-            if (vec16) {                          // 16 bytes per copy: 2 copies per thread per tile
+    // the loader's per-thread pattern is the same for every tile: precompute it
+    constexpr int CHUNKS = DW * (ER_TT / 4) / ER_THREADS;           // 16-byte copies per thread per tile (2 or 4)
+    int64_t g_off[CHUNKS];
+    int s_off[CHUNKS], t_of[CHUNKS];
 #pragma unroll
-                for (int i = tid; i < E_DS * (E_TT / 4); i += EA_THREADS) {
-                    const int d = i >> 5, t = (i & 31) * 4;
-                    float* dst = Xs + d * EA_XS + t;
-                    if (d < dn && t < tt) cp_async16(dst, x + (size_t(n) * D + d0 + d) * T + t0 + t);   // T % 4 == 0: a chunk never straddles tt
-                    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+    for (int r = 0; r < CHUNKS; ++r) {
+        const int i = tid + r * ER_THREADS, d = i >> 4, t = (i & 15) * 4;
+        g_off[r] = int64_t(d0 + d) * T + t;
+        s_off[r] = d * ER_XS + t;
+        t_of[r] = d < dn ? t : ER_TT;                               // depths beyond D are never copied (nor read)
+    }
+    // tile -> (utterance, first frame), advanced incrementally (no 64-bit division in the loop)
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    int64_t ld_tile = first;
+    int64_t ld_n = first / tiles_per_utt;
+    int ld_j = int(first % tiles_per_utt);
+
+    auto issue = [&](int st) {
+        float* Xs = reinterpret_cast<float*>(stage0 + size_t(st) * STAGE_BYTES);
+        int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + DW * ER_XS);
+        float* s_mask = reinterpret_cast<float*>(s_idx + ER_TT);
+        if (ld_tile < n_tiles) {
+            const int64_t t0 = int64_t(ld_j) * ER_TT;
+            const int tt = int(min(int64_t(ER_TT), T - t0));
+            const float* src = x + ld_n * int64_t(D) * T + t0;
+            if (vec16) {
+#pragma unroll
+                for (int r = 0; r < CHUNKS; ++r)
+                    if (t_of[r] < tt) cp_async16(Xs + s_off[r], src + g_off[r]);              // T % 4 == 0: never straddles tt
             } else {
-#pragma unroll
-                for (int i = tid; i < E_DS * E_TT; i += EA_THREADS) {
-                    const int d = i >> 7, t = i & (E_TT - 1);
-                    float* dst = Xs + d * EA_XS + t;
-                    if (d < dn && t < tt) cp_async4(dst, x + (size_t(n) * D + d0 + d) * T + t0 + t);
-                    else *dst = 0.f;
+                for (int i = tid; i < dn * ER_TT; i += ER_THREADS) {
+                    const int d = i >> 6, t = i & (ER_TT - 1);
+                    if (t < tt) cp_async4(Xs + d * ER_XS + t, src + int64_t(d0 + d) * T + t);
                 }
             }
-            if (tid < E_TT) {
+            if (tid < ER_TT) {
                 if (tid < tt) {
-                    cp_async8(s_idx + tid, idx + n * T + t0 + tid);
-                    if (mask) cp_async4(s_mask + tid, mask + n * T + t0 + tid);
+                    cp_async8(s_idx + tid, idx + ld_n * T + t0 + tid);
+                    if (mask) cp_async4(s_mask + tid, mask + ld_n * T + t0 + tid);
                     else s_mask[tid] = 1.f;
                 } else {
-                    s_idx[tid] = -1;
+                    s_idx[tid] = -1;               // frames beyond the utterance: no row (their x slots are never read)
                     s_mask[tid] = 0.f;
                 }
             }
         }
         cp_async_commit();
+        ld_tile += step;
+        ld_j += int(step % tiles_per_utt);
+        ld_n += step / tiles_per_utt;
+        if (ld_j >= tiles_per_utt) { ld_j -= tiles_per_utt; ++ld_n; }
     };
 
-    const int64_t first = blockIdx.x, step = gridDim.x;
+    // keys of a tile: (code << 8) | frame for valid rows, ~0u otherwise; 64 keys = 2 per lane, bitonic sort in one warp
+    auto sort_tile = [&](bool exists, int st, uint32_t* out) {
+        if (!exists) return;
+        const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(st) * STAGE_BYTES);
+        const int64_t* s_idx = reinterpret_cast<const int64_t*>(Xs + DW * ER_XS);
+        const float* s_mask = reinterpret_cast<const float*>(s_idx + ER_TT);
+        uint32_t key[2];
 #pragma unroll
-    for (int s = 0; s < EA_STAGES - 1; ++s) issue(first + s * step, s);
+        for (int r = 0; r < 2; ++r) {
+            const int t = r * 32 + lane;
+            const int64_t ci = s_idx[t];
+            key[r] = (s_mask[t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int k = 2; k <= ER_TT; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {                     // j == 32, k == 64: partner is the lane's other key, ascending
+                    const uint32_t a = key[0], b = key[1];
+                    key[0] = min(a, b);
+                    key[1] = max(a, b);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                        const int i = r * 32 + lane;
+                        const bool up = (i & k) == 0, lower = (lane & j) == 0;
+                        key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                    }
+                }
+            }
+        }
+        out[lane] = key[0];
+        out[32 + lane] = key[1];
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    cp_async_wait<STAGES - 2>();                   // tile 0 has landed
+    __syncthreads();
+    if (warp == ER_WARPS - 1) sort_tile(first < n_tiles, 0, sorted);
 
     int it = 0;
-    int pc[4] = {-1, -1, -1, -1};                // pending (code, partial sum, count) of this warp's four chains
-    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pn[4] = {0.f, 0.f, 0.f, 0.f};
     for (int64_t tile = first; tile < n_tiles; tile += step, ++it) {
-        cp_async_wait<EA_STAGES - 2>();          // this tile's group has landed (for this thread's copies)
-        __syncthreads();                         // ... for everyone's; and the stage freed last iteration is reusable
-        issue(tile + int64_t(EA_STAGES - 1) * step, (it + EA_STAGES - 1) % EA_STAGES);
-        const int st = it % EA_STAGES;
-        const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(st) * EA_STAGE_BYTES);
-        const int64_t* s_idx = reinterpret_cast<const int64_t*>(Xs + E_DS * EA_XS);
-        const float* s_mask = reinterpret_cast<const float*>(s_idx + E_TT);
-        const float* xcol = Xs + lane * EA_XS;
-        int code[4];
-        unsigned m[4];
+        cp_async_wait<STAGES - 3>();               // tiles it and it+1 have landed (this thread's copies)
+        __syncthreads();                           // ... everyone's; sorted[it & 1] is complete; stage of tile it-1 is free
+        issue((it + STAGES - 1) % STAGES);
+        if (warp == ER_WARPS - 1) {
+            sort_tile(tile + step < n_tiles, (it + 1) % STAGES, sorted + ((it + 1) & 1) * ER_TT);
+        } else {
+            const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(it % STAGES) * STAGE_BYTES);
+            const uint32_t* keys = sorted + (it & 1) * ER_TT;
+            const int lo = warp * ER_PER, hi = min(ER_TT, lo + ER_PER);
+            int i = lo;
+            const uint32_t kprev = (lo > 0 && lo < ER_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
+            // skip the tail of a run that started in an earlier warp's range
+            while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
+            while (i < hi) {
+                uint32_t key = keys[i];
+                if (key == 0xFFFFFFFFu) break;                                // sorted: no more rows
+                const uint32_t code = key >> 8;
+                float a[NQ];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t = j * 32 + lane;
-            const int64_t ci = s_idx[t];
-            code[j] = (s_mask[t] != 0.f && ci >= 0) ? int(min(ci, int64_t(K - 1))) : -1;
-            m[j] = __ballot_sync(0xffffffffu, code[j] >= 0 && (code[j] & (EA_WARPS - 1)) == warp);
-        }
-        // Four independent chains (one per 32-frame group), each with its own pending (code, sum, count): the shuffles
-        // and column reads of a step are issued together, so their latency is paid once per step, not once per row.
-        while (m[0] | m[1] | m[2] | m[3]) {
-            int c[4];
-            float v[4];
+                for (int q = 0; q < NQ; ++q) a[q] = 0.f;
+                float cnt = 0.f;
+                do {                                                          // one run; may continue past hi
+                    const float* col = Xs + (key & 255u);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                c[j] = -1;
-                v[j] = 0.f;
-                if (m[j]) {                       // warp-uniform
-                    const int b = __ffs(m[j]) - 1;
-                    m[j] &= m[j] - 1;
-                    c[j] = __shfl_sync(0xffffffffu, code[j], b);
-                    v[j] = xcol[j * 32 + b];
-                }
-            }
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane + 32 * q < dn) a[q] += col[(lane + 32 * q) * ER_XS];
+                    cnt += 1.f;
+                    ++i;
+                    key = i < ER_TT ? keys[i] : 0xFFFFFFFFu;
+                } while (key != 0xFFFFFFFFu && (key >> 8) == code);
+#if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 256)      /* timing experiment: no updates */
+                if (a[0] + cnt == -12345.f) sums[0] = 1.f;
+#else
+                if (SLAB) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (c[j] < 0) continue;
-                if (c[j] != pc[j]) {              // runs of one code (hot codes!) collapse into a register sum
-                    if (pc[j] >= 0) {
-                        acc[size_t(pc[j]) * E_DS + lane] += ps[j];
-                        if (count_here && lane == 0) cnt[pc[j]] += pn[j];
-                    }
-                    pc[j] = c[j]; ps[j] = v[j]; pn[j] = 1.f;
+                    for (int q = 0; q < NQ; ++q) slab[size_t(code) * DW + lane + 32 * q] += a[q];
+                    if (count_here && lane == 0) scnt[code] += cnt;
                 } else {
-                    ps[j] += v[j]; pn[j] += 1.f;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane + 32 * q < dn) atomicAdd(&sums[size_t(code) * D + lane + 32 * q], a[q]);
+                    if (lane == 0) atomicAdd(&counts[code], cnt);
                 }
+#endif
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (pc[j] >= 0) {
-            acc[size_t(pc[j]) * E_DS + lane] += ps[j];
-            if (count_here && lane == 0) cnt[pc[j]] += pn[j];
-        }
     cp_async_wait<0>();
-    __syncthreads();
-    // flush the private slab: one FP32 reduction per touched cell, coalesced along depth
-    float* sums = stats;
-    float* counts = stats + size_t(K) * D;
-    for (int i = tid; i < K * E_DS; i += EA_THREADS) {
-        const int c = i / E_DS, d = i % E_DS;
-        const float v = acc[i];
-        if (d < dn && v != 0.f) atomicAdd(&sums[size_t(c) * D + d0 + d], v);
+    if (SLAB) {
+        __syncthreads();
+        for (int i = tid; i < K * DW; i += ER_THREADS) {
+            const int c = i / DW, d = i % DW;
+            const float v = slab[i];
+            if (d < dn && v != 0.f) atomicAdd(&sums[size_t(c) * D + d0 + d], v);
+        }
+        if (count_here)
+            for (int c = tid; c < K; c += ER_THREADS)
+                if (scnt[c] != 0.f) atomicAdd(&counts[c], scnt[c]);
     }
-    if (count_here)
-        for (int c = tid; c < K; c += EA_THREADS)
-            if (cnt[c] != 0.f) atomicAdd(&counts[c], cnt[c]);
 }
 
 // Large-K variant: rows of one tile rarely share a code, so privatisation buys nothing; transpose the

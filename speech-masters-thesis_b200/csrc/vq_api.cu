@@ -213,18 +213,25 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
     VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t tiles = N * ((T + E_TT - 1) / E_TT);
-    const size_t smem = size_t(EA_STAGES) * EA_STAGE_BYTES + (size_t(K) * E_DS + K) * 4;
-    if (smem <= 220 * 1024) {
+    const int64_t tiles_r = N * ((T + ER_TT - 1) / ER_TT);
+    if (K < (1 << 24) && er_smem_bytes<true>(K) <= 227 * 1024) {
+        // private [K][64] slab per (row chunk, 64-deep slice); one CTA per SM
         static bool configured = false;
         if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             configured = true;
         }
-        const int slices = int((D + E_DS - 1) / E_DS);
-        // one CTA per SM: a private slab per (row chunk, depth slice); few enough chunks that the flush stays small
-        int gx = int(std::min<int64_t>(tiles, std::max<int64_t>(1, num_sms() / slices)));
-        dim3 grid(gx, slices);
-        ema_accumulate_smem_kernel<<<grid, EA_THREADS, smem, stream>>>(x, idx, mask, N, int(D), T, K, stats);
+        const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
+        const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, num_sms() / slices)));
+        ema_accumulate_runs_kernel<true><<<dim3(gx, slices), ER_THREADS, er_smem_bytes<true>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats);
+    } else if (K < (1 << 24) && D <= ErCfg<false>::DW) {
+        static bool configured = false;
+        if (!configured) {
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        const int grid = int(std::min<int64_t>(tiles_r, num_sms()));
+        ema_accumulate_runs_kernel<false><<<grid, ER_THREADS, er_smem_bytes<false>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats);
     } else {
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 8));
         ema_accumulate_global_kernel<<<grid, E_THREADS, 0, stream>>>(x, idx, mask, N, int(D), T, K, stats);
