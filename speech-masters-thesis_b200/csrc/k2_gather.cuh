@@ -9,13 +9,16 @@
 
 namespace vq {
 
-constexpr int G_TT = 64;          // frames per tile
+constexpr int G_TT = 64;          // frames per tile (128-frame tiles measured no faster and need twice the shared memory)
 constexpr int G_THREADS = 256;
 
 enum GatherMode { GM_FWD = 0, GM_BWD = 1, GM_DECODE = 2 };
 
-// Shared memory: Es[G_TT][Ds] floats with Ds odd, + idx/mask staging.
-template <int MODE>
+// Shared memory: gathered codebook rows + idx/mask staging.
+//   VEC = false: Es[frame][Ds] (Ds odd), 4-byte accesses along frames -- any T / alignment.
+//   VEC = true : Es[depth][G_TT + 4], 16-byte accesses along frames (T % 4 == 0, 16-byte aligned tensors): a warp moves
+//                512 contiguous bytes per request and a thread has 8 independent 16-byte loads in flight.
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(G_THREADS)
 gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
               const float* __restrict__ k, const float* __restrict__ grad_xq, const float* __restrict__ grad_commit,
@@ -23,9 +26,10 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
               float* __restrict__ out, double* __restrict__ scalars, float* __restrict__ results,
               unsigned int total_blocks) {
     extern __shared__ __align__(16) float smem[];
-    float* Es = smem;                                   // [G_TT][Ds]
-    int* s_idx = reinterpret_cast<int*>(Es + size_t(G_TT) * Ds);   // [G_TT]
-    float* s_mask = reinterpret_cast<float*>(s_idx + G_TT);        // [G_TT]
+    float* Es = smem;                                   // [G_TT][Ds] or [D][G_TT + 4]
+    const size_t es_floats = ((VEC ? size_t(D) * (G_TT + 4) : size_t(G_TT) * Ds) + 3) & ~size_t(3);
+    float* s_mask = Es + es_floats;                                // [G_TT], 16-byte aligned (read as float4)
+    int* s_idx = reinterpret_cast<int*>(s_mask + G_TT);            // [G_TT]
     __shared__ double red[32];
     __shared__ bool is_last;
 
@@ -58,43 +62,102 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
             if (MODE == GM_FWD) msum_local += double(m);
         }
         __syncthreads();
-        // ---- gather: one warp per row, coalesced 128-byte reads of the codebook row (L2-resident)
-        for (int r = warp; r < tt; r += G_THREADS / 32) {
-            const float* src = k + size_t(s_idx[r]) * D;
-            float* dst = Es + size_t(r) * Ds;
-            for (int d = lane; d < D; d += 32) dst[d] = __ldg(src + d);
-        }
-        __syncthreads();
-        // ---- stream: lanes along frames (coalesced), warps along depth
-        const int t = tid & (G_TT - 1);
-        const int dgrp = tid / G_TT;                       // 0..3
-        if (t < tt) {
-            const float m = s_mask[t];
-            const bool valid = m != 0.f;
-            const float* er = Es + size_t(t) * Ds;
-            const size_t base = (size_t(n) * D) * T + t0 + t;
-            float acc = 0.f;
+        if (VEC) {
+            constexpr int ES = G_TT + 4;
+            // ---- gather: one warp per frame, coalesced reads of the codebook row, transposed into Es[depth][frame]
+            for (int r = warp; r < tt; r += G_THREADS / 32) {
+                const float* src = k + size_t(s_idx[r]) * D;
+                for (int d = lane; d < D; d += 32) Es[d * ES + r] = __ldg(src + d);
+            }
+            __syncthreads();
+            // ---- stream: G_TT/4 threads cover the frames of one depth with float4
+            constexpr int TQ = G_TT / 4;                     // float4 groups per depth row
+            const int t4 = (tid % TQ) * 4, dg = tid / TQ;
+            if (t4 < tt) {
+                const float4 m4 = *reinterpret_cast<const float4*>(s_mask + t4);
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float vv[4] = {m4.x != 0.f ? 1.f : 0.f, m4.y != 0.f ? 1.f : 0.f, m4.z != 0.f ? 1.f : 0.f, m4.w != 0.f ? 1.f : 0.f};
+                const size_t base = (size_t(n) * D) * T + t0 + t4;
+                float acc_all = 0.f, acc_valid = 0.f;
 #pragma unroll 4
-            for (int d = dgrp; d < D; d += G_THREADS / G_TT) {
-                const size_t o = base + size_t(d) * T;
-                const float e = er[d];
-                if (MODE == GM_DECODE) {
-                    st_stream(out + o, e);
-                } else {
-                    const float xv = ld_stream(x + o);
-                    if (MODE == GM_FWD) {
-                        const float diff = __fsub_rn(e, xv);              // (x_d - x)
-                        st_stream(out + o, __fmul_rn(__fadd_rn(xv, diff), m));   // (x + (x_d - x)) * mask
-                        acc = fmaf(diff, diff, acc);
+                for (int d = dg; d < D; d += G_THREADS / TQ) {
+                    const size_t o = base + size_t(d) * T;
+                    const float4 e4 = *reinterpret_cast<const float4*>(Es + d * ES + t4);
+                    const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+                    float oo[4];
+                    if (MODE == GM_DECODE) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) oo[j] = ee[j];
                     } else {
-                        float g = grad_xq ? __fmul_rn(ld_stream(grad_xq + o), m) : 0.f;
-                        if (valid) g = fmaf(gscale, __fsub_rn(xv, e), g);
-                        st_stream(out + o, g);
+                        const float4 x4 = ld_stream4(reinterpret_cast<const float4*>(x + o));
+                        const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+                        if (MODE == GM_FWD) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float diff = __fsub_rn(ee[j], xx[j]);                   // (x_d - x)
+                                oo[j] = __fmul_rn(__fadd_rn(xx[j], diff), mm[j]);             // (x + (x_d - x)) * mask
+                                const float d2 = diff * diff;
+                                acc_all += d2;
+                                acc_valid = fmaf(d2, vv[j], acc_valid);
+                            }
+                        } else {
+                            float gg[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (grad_xq) {
+                                const float4 g4 = ld_stream4(reinterpret_cast<const float4*>(grad_xq + o));
+                                gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float g = __fmul_rn(gg[j], mm[j]);
+                                if (vv[j] != 0.f) g = fmaf(gscale, __fsub_rn(xx[j], ee[j]), g);
+                                oo[j] = g;
+                            }
+                        }
+                    }
+                    st_stream4(reinterpret_cast<float4*>(out + o), make_float4(oo[0], oo[1], oo[2], oo[3]));
+                }
+                sq_all += double(acc_all);
+                sq += double(acc_valid);
+            }
+        } else {
+            // ---- gather: one warp per row, coalesced 128-byte reads of the codebook row (L2-resident)
+            for (int r = warp; r < tt; r += G_THREADS / 32) {
+                const float* src = k + size_t(s_idx[r]) * D;
+                float* dst = Es + size_t(r) * Ds;
+                for (int d = lane; d < D; d += 32) dst[d] = __ldg(src + d);
+            }
+            __syncthreads();
+            // ---- stream: lanes along frames (coalesced), warps along depth
+            const int t = tid & (G_TT - 1);
+            const int dgrp = tid / G_TT;                       // 0..3
+            if (t < tt) {
+                const float m = s_mask[t];
+                const bool valid = m != 0.f;
+                const float* er = Es + size_t(t) * Ds;
+                const size_t base = (size_t(n) * D) * T + t0 + t;
+                float acc = 0.f;
+#pragma unroll 4
+                for (int d = dgrp; d < D; d += G_THREADS / G_TT) {
+                    const size_t o = base + size_t(d) * T;
+                    const float e = er[d];
+                    if (MODE == GM_DECODE) {
+                        st_stream(out + o, e);
+                    } else {
+                        const float xv = ld_stream(x + o);
+                        if (MODE == GM_FWD) {
+                            const float diff = __fsub_rn(e, xv);              // (x_d - x)
+                            st_stream(out + o, __fmul_rn(__fadd_rn(xv, diff), m));   // (x + (x_d - x)) * mask
+                            acc = fmaf(diff, diff, acc);
+                        } else {
+                            float g = grad_xq ? __fmul_rn(ld_stream(grad_xq + o), m) : 0.f;
+                            if (valid) g = fmaf(gscale, __fsub_rn(xv, e), g);
+                            st_stream(out + o, g);
+                        }
                     }
                 }
+                sq_all += double(acc);                    // ||k[idx] - x||^2 of EVERY row: the numerator of `fit`
+                if (valid) sq += double(acc);
             }
-            sq_all += double(acc);                    // ||k[idx] - x||^2 of EVERY row: the numerator of `fit`
-            if (valid) sq += double(acc);
         }
     }
     if (MODE == GM_FWD) {
