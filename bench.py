@@ -333,13 +333,14 @@ def run_b200(args):
     res = torch.zeros(8, device=dev)
     stats = torch.zeros(K_BINS * EMB + K_BINS, device=dev)
     g_commit = torch.ones((), device=dev)
+    k3_scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=dev)
     k_sum, k_elem, k_new = kd.clone(), torch.ones(K_BINS, device=dev), torch.empty_like(kd)
     k2_fwd = timed(lambda: lib.vq_gather_st_fwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K_BINS,
                                                 x_q.data_ptr(), scalars.data_ptr(), res.data_ptr(), stream))
     k2_bwd = timed(lambda: lib.vq_gather_st_bwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), x_q.data_ptr(),
                                                 g_commit.data_ptr(), scalars.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
     k2_dec = timed(lambda: lib.vq_decode(idx.data_ptr(), kd.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
-    k3_acc = timed(lambda: lib.vq_ema_accumulate(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), n, d, t, K_BINS, stats.data_ptr(), stream))
+    k3_acc = timed(lambda: lib.vq_ema_accumulate(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), n, d, t, K_BINS, stats.data_ptr(), k3_scratch.data_ptr(), stream))
     k3_fin = timed(lambda: lib.vq_ema_finalize(stats.data_ptr(), kd.data_ptr(), kd.data_ptr(), k_new.data_ptr(), k_sum.data_ptr(),
                                                k_elem.data_ptr(), K_BINS, EMB, 0.99, 1.0, 0.0, scalars.data_ptr(), res.data_ptr(), None, stream))
 

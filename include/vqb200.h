@@ -123,10 +123,11 @@ int vq_decode(const int64_t* idx, const float* k, int64_t n_utt, int64_t emb_wid
 /* K3a -- replaces the dense one-hot scatter + GEMM + row-sum of update_k (bottleneck.py:64-68).
  *   stats is [K*D + K] fp32: per-code sums of the valid rows followed by per-code counts.
  *   The call ADDS into stats (zero it first); it is the buffer the caller all-reduces over NCCL
- *   (bottleneck.py:74-75) before vq_ema_finalize. */
+ *   (bottleneck.py:74-75) before vq_ema_finalize.  scratch (may be NULL) is ceil(T/64)*N bytes of device memory;
+ *   when given together with a mask, 64-frame tiles without a valid frame are never read. */
 int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask,
                       int64_t n_utt, int64_t emb_width, int64_t t_frames, int k_bins,
-                      float* stats, void* stream);
+                      float* stats, void* scratch, void* stream);
 
 /* K3b -- replaces the EMA lerp, usage threshold, dead-code revival and the four metrics of update_k
  * (bottleneck.py:78-89).  k_sum, k_elem are updated in place; the new codebook is written to k, which may

@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvqb200.so")
+LIB_PATH = os.environ.get("VQB200_LIB", os.path.join(_HERE, "lib", "libvqb200.so"))   # override only for A/B experiments
 
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC}
@@ -37,7 +37,7 @@ SIGNATURES = {
     "vq_gather_st_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                   _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p]),
     "vq_decode": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p]),
-    "vq_ema_accumulate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p]),
+    "vq_ema_accumulate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "vq_ema_finalize": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                  _c_double, _c_double, _c_double, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "vq_gather_rows": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_void_p, _c_void_p]),

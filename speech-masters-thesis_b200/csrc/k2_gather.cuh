@@ -19,7 +19,7 @@ enum GatherMode { GM_FWD = 0, GM_BWD = 1, GM_DECODE = 2 };
 //   VEC = true : Es[depth][G_TT + 4], 16-byte accesses along frames (T % 4 == 0, 16-byte aligned tensors): a warp moves
 //                512 contiguous bytes per request and a thread has 8 independent 16-byte loads in flight.
 template <int MODE, bool VEC>
-__global__ void __launch_bounds__(G_THREADS)
+__global__ void __launch_bounds__(G_THREADS, VEC ? 4 : 6)      // the kernel is latency-bound: 6 resident CTAs (40 registers) beat 5
 gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
               const float* __restrict__ k, const float* __restrict__ grad_xq, const float* __restrict__ grad_commit,
               int64_t N, int D, int64_t T, int K, int Ds,
@@ -136,7 +136,7 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
                 const float* er = Es + size_t(t) * Ds;
                 const size_t base = (size_t(n) * D) * T + t0 + t;
                 float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 8
                 for (int d = dgrp; d < D; d += G_THREADS / G_TT) {
                     const size_t o = base + size_t(d) * T;
                     const float e = er[d];

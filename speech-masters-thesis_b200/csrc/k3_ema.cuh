@@ -40,6 +40,20 @@ constexpr int ER_WARPS = 16;                 // warp 15 sorts, warps 0..14 accum
 constexpr int ER_THREADS = ER_WARPS * 32;
 constexpr int ER_PER = (ER_TT + ER_WARPS - 2) / (ER_WARPS - 1);   // sorted rows per accumulating warp (5)
 
+// flags[tile] = 1 when the 64-frame tile has at least one valid frame: padded tiles (35 % of an LJSpeech-like batch) are
+// then never loaded.  One warp per tile.
+__global__ void __launch_bounds__(256) ema_tile_flags_kernel(const float* __restrict__ mask, int64_t N, int64_t T, int tiles_per_utt,
+                                                            unsigned char* __restrict__ flags) {
+    const int64_t tile = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= N * tiles_per_utt) return;
+    const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * ER_TT;
+    bool any = false;
+    for (int t = lane; t < ER_TT && t0 + t < T; t += 32) any |= mask[n * T + t0 + t] != 0.f;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[tile] = any ? 1 : 0;
+}
+
 template <bool SLAB> struct ErCfg;
 template <> struct ErCfg<true>  { static constexpr int DW = 64,  STAGES = 5; };   // depth slice width, ring depth
 template <> struct ErCfg<false> { static constexpr int DW = 128, STAGES = 6; };
@@ -51,7 +65,8 @@ template <bool SLAB> inline size_t er_smem_bytes(int K) {
 template <bool SLAB>
 __global__ void __launch_bounds__(ER_THREADS, 1)
 ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
-                           int64_t N, int D, int64_t T, int K, float* __restrict__ stats) {
+                           int64_t N, int D, int64_t T, int K, float* __restrict__ stats,
+                           const unsigned char* __restrict__ tile_flags) {
     constexpr int DW = ErCfg<SLAB>::DW, STAGES = ErCfg<SLAB>::STAGES, NQ = DW / 32, STAGE_BYTES = er_stage_bytes<SLAB>();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* stage0 = smem_raw;
@@ -89,12 +104,17 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
     int64_t ld_tile = first;
     int64_t ld_n = first / tiles_per_utt;
     int ld_j = int(first % tiles_per_utt);
+    const int step_j = int(step % tiles_per_utt);
+    const int64_t step_n = step / tiles_per_utt;
+    unsigned char ld_flag = (tile_flags && first < n_tiles) ? tile_flags[first] : 1;
 
     auto issue = [&](int st) {
         float* Xs = reinterpret_cast<float*>(stage0 + size_t(st) * STAGE_BYTES);
         int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + DW * ER_XS);
         float* s_mask = reinterpret_cast<float*>(s_idx + ER_TT);
-        if (ld_tile < n_tiles) {
+        if (ld_tile < n_tiles && ld_flag == 0) {
+            if (tid < ER_TT) { s_idx[tid] = -1; s_mask[tid] = 0.f; }      // nothing valid here: no rows, no loads
+        } else if (ld_tile < n_tiles) {
             const int64_t t0 = int64_t(ld_j) * ER_TT;
             const int tt = int(min(int64_t(ER_TT), T - t0));
             const float* src = x + ld_n * int64_t(D) * T + t0;
@@ -121,9 +141,11 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
         }
         cp_async_commit();
         ld_tile += step;
-        ld_j += int(step % tiles_per_utt);
-        ld_n += step / tiles_per_utt;
+        ld_j += step_j;
+        ld_n += step_n;
         if (ld_j >= tiles_per_utt) { ld_j -= tiles_per_utt; ++ld_n; }
+        // the flag of the tile after this one is fetched now and consumed by the next call (latency off the issue path)
+        ld_flag = (tile_flags && ld_tile < n_tiles) ? tile_flags[ld_tile] : 1;
     };
 
     // keys of a tile: (code << 8) | frame for valid rows, ~0u otherwise; 64 keys = 2 per lane, bitonic sort in one warp

@@ -8,6 +8,7 @@
 #include "k3_ema.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 using namespace vq;
@@ -53,7 +54,10 @@ static int launch_gather(const float* x, const int64_t* idx, const float* mask, 
                          float* results, cudaStream_t stream) {
     auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     // measured on B200 (K=512, D=128): 16-byte accesses help the backward (3 streams) and decode, not the forward
-    const bool vec = MODE != GM_FWD && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) && aligned(mask);
+    // measured on B200 (K=512, D=128): the 16-byte path wins for the backward (three streams), the 4-byte path elsewhere
+    bool vec = MODE == GM_BWD && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) && aligned(mask);
+    static const char* force = getenv("VQ_K2_VEC");          // A/B switch for experiments: 0 = 4-byte path, 1 = 16-byte path
+    if (force && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) && aligned(mask)) vec = force[0] == '1';
     if (vec) return launch_gather_v<MODE, true>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
     return launch_gather_v<MODE, false>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
 }
@@ -218,7 +222,7 @@ int vq_decode(const int64_t* idx, const float* k, int64_t N, int64_t D, int64_t 
 }
 
 int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int64_t N, int64_t D, int64_t T, int K,
-                      float* stats, void* stream_) {
+                      float* stats, void* scratch, void* stream_) {
     if (check_shape(N, D, T, K)) return 1;
     if (N * T == 0) return 0;
     VQ_REQUIRE(x && idx && stats, "null pointer");
@@ -226,6 +230,13 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t tiles = N * ((T + E_TT - 1) / E_TT);
     const int64_t tiles_r = N * ((T + ER_TT - 1) / ER_TT);
+    unsigned char* flags = nullptr;
+    if (mask && scratch) {          // one byte per 64-frame tile: tiles without a valid frame are skipped
+        flags = static_cast<unsigned char*>(scratch);
+        const int tpu = int((T + ER_TT - 1) / ER_TT);
+        ema_tile_flags_kernel<<<unsigned((tiles_r * 32 + 255) / 256), 256, 0, stream>>>(mask, N, T, tpu, flags);
+        VQ_CUDA_OK(cudaGetLastError());
+    }
     if (K < (1 << 24) && er_smem_bytes<true>(K) <= 227 * 1024) {
         // private [K][64] slab per (row chunk, 64-deep slice); one CTA per SM
         static bool configured = false;
@@ -235,7 +246,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
         }
         const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
         const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, num_sms() / slices)));
-        ema_accumulate_runs_kernel<true><<<dim3(gx, slices), ER_THREADS, er_smem_bytes<true>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats);
+        ema_accumulate_runs_kernel<true><<<dim3(gx, slices), ER_THREADS, er_smem_bytes<true>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats, flags);
     } else if (K < (1 << 24) && D <= ErCfg<false>::DW) {
         static bool configured = false;
         if (!configured) {
@@ -243,7 +254,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
             configured = true;
         }
         const int grid = int(std::min<int64_t>(tiles_r, num_sms()));
-        ema_accumulate_runs_kernel<false><<<grid, ER_THREADS, er_smem_bytes<false>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats);
+        ema_accumulate_runs_kernel<false><<<grid, ER_THREADS, er_smem_bytes<false>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats, flags);
     } else {
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 8));
         ema_accumulate_global_kernel<<<grid, E_THREADS, 0, stream>>>(x, idx, mask, N, int(D), T, K, stats);

@@ -215,7 +215,8 @@ class BottleneckBlock(nn.Module):
                 k_rand = self._restart_rows_nct(x, mask)
             stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):
-                check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), _stream(x)),
+                scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=x.device) if mask is not None else None
+                check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), ptr(scratch), _stream(x)),
                       "vq_ema_accumulate")
             # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
             # here ONE all-reduce of the packed buffer (see dist.py)

@@ -303,7 +303,7 @@ def test_full_size_properties(vq):
     lib = vq._lib.load()
     stats = torch.zeros(K * D + K, device=DEV)
     rc = lib.vq_ema_accumulate(xd.data_ptr(), z.data_ptr(), md.data_ptr(), n, D, x.shape[2], K, stats.data_ptr(),
-                               torch.cuda.current_stream().cuda_stream)
+                               None, torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.vq_last_error()
     assert float(stats[K * D:].sum()) == float(mask.sum())
     col = (xd * md).double().sum(dim=(0, 2))
@@ -334,7 +334,7 @@ def test_large_codebook_paths(vq):
     stats = torch.zeros(K * D + K, device=DEV)
     z, xd, md = o_l.view(3, -1).to(DEV), x.to(DEV), mask.to(DEV)      # keep the device tensors alive across the call
     rc = lib.vq_ema_accumulate(xd.data_ptr(), z.data_ptr(), md.data_ptr(), 3, D, x.shape[2], K,
-                               stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                               stats.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
     close(stats[:K * D].view(K, D), s_sum, rtol=1e-5, atol=1e-5)
