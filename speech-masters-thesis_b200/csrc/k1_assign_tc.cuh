@@ -11,8 +11,8 @@
 //                 A buffers (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and
 //                 the FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) a few tiles later: merge the two
 //                 scan groups' candidates, run the provable safety test, write idx (optionally re-score in FP32)
-//   warps 4-11    scan groups: tcgen05.ld the accumulators (thread == frame; each group takes 64 of the 128 code
-//                 columns) and keep a branch-free running (best, runner-up) over integer keys
+//   warps 4-11    scan groups: tcgen05.ld the accumulators (thread == frame; the two groups take alternate 128-code
+//                 tiles) and keep a branch-free running (best, runner-up) over integer keys
 //
 // Keys.  The score of code c for frame r is s = x.e_c - ||e_c||^2/2 (argmax s == argmin distance).  The scan computes
 // t = acc - (||e_c||^2/2 - B) with B = 1.5 * 2^E, E chosen per launch so that every in-range score lands in
@@ -268,7 +268,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
         for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
-        for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 8); }
+        for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 4); }
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -529,41 +529,49 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
-                const uint32_t s = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
-                const int cbase = nt * TN + wg * 64;
+                // The two scan groups take ALTERNATE code tiles (accumulator stage == group), so one group's TMEM loads and
+                // barrier waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
+                if ((qa & 1u) != uint32_t(wg)) continue;
+                const uint32_t s = qa & 1u, sph = (qa >> 1) & 1u;
                 mbar_wait<20>(smem_u32(&ctl->acc_full[s]), sph);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4) VQ_TRACE_NT(12, it, nt);
-                uint32_t v0[32], v1[32];
-                const uint32_t taddr = tmem + lane_base + s * TN + wg * 64;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cbase = nt * TN + half * 64;
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr = tmem + lane_base + s * TN + half * 64;
 #if VQ_EXPERIMENT & 2                     /* timing experiment: no TMEM reads */
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { v0[j] = taddr + j; v1[j] = taddr * 3 + j; }
+                    for (int j = 0; j < 32; ++j) { v0[j] = taddr + j; v1[j] = taddr * 3 + j; }
 #else
-                tc_ld32(taddr, v0);
-                tc_ld32(taddr + 32, v1);
-                tc_wait_ld();
+                    tc_ld32(taddr, v0);
+                    tc_ld32(taddr + 32, v1);
+                    tc_wait_ld();
 #endif
-                tc_fence_before();
-                mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                    // accumulators are in registers: free the stage
-                if (warp == 4) VQ_TRACE_NT(13, it, nt);
-                uint32_t t1, t2;
+                    if (half == 1) {
+                        tc_fence_before();
+                        mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));            // all 128 columns are in registers: free the stage
+                        if (warp == 4) VQ_TRACE_NT(13, it, nt);
+                    }
+                    uint32_t t1, t2;
 #if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
-                t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
+                    t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
 #else
-                if (p.hn_in_smem) scan64<true>(v0, v1, hn_s + cbase, key_mul, t1, t2);
-                else scan64<false>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
+                    if (p.hn_in_smem) scan64<true>(v0, v1, hn_s + cbase, key_mul, t1, t2);
+                    else scan64<false>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
 #endif
-                if (warp == 4) VQ_TRACE_NT(14, it, nt);
-                // fold the tile-local pair into the running pair
-                if (t1 > r1) {
-                    r2 = max(r1, t2);
-                    r1 = t1;
-                    rc1 = cbase + int(t1 & 63u);
-                } else {
-                    r2 = max(r2, t1);
+                    // fold the pair of this half tile into the running pair
+                    if (t1 > r1) {
+                        r2 = max(r1, t2);
+                        r1 = t1;
+                        rc1 = cbase + int(t1 & 63u);
+                    } else {
+                        r2 = max(r2, t1);
+                    }
                 }
+                if (warp == 4) VQ_TRACE_NT(14, it, nt);
             }
             const uint32_t cb = it % CD, cph = (it / CD) & 1;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
@@ -635,7 +643,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
     p.n_tiles = int(n_tiles);
     p.n_nt = w.Kp / TN; p.n_kb = w.Dp / BKB; p.n_xch = w.Dp / XCH;
-    p.acc_stages = 2;                                           // (3 stages with 2 A buffers measured slower than 2 stages with 4)
+    p.acc_stages = 2;                                           // one accumulator stage per scan group
     p.a_bufs = std::min(A_BUFS_MAX, (512 - p.acc_stages * TN) / (w.Dp / 2));   // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, CD - 1);                         // the back stage trails the front stage by this many tiles
     p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
