@@ -70,6 +70,9 @@ struct Params {
     int N, D, Dp, K, Kp, T;
     int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, acc_stages, lag, resident, b_stages, vec_k;
     int hn_in_smem;
+    int fold;                // -(||e||^2/2 - B) rides in the MMA as one extra k-step (resident codebooks only): no FADD, no loads in the scan
+    int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
+    int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
 };
 
@@ -143,6 +146,10 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -165,6 +172,17 @@ __device__ __forceinline__ uint64_t b_desc_base(uint32_t smem_addr) {
     d |= uint64_t(2) << 61;                              // SWIZZLE_128B
     return d;
 }
+// UMMA descriptor of the folded -(||e||^2/2 - B) tile: K-major, no swizzle, 128 codes x 16 fp16 stored as
+// [16 row groups][2 k halves][8 rows][8 fp16] (core matrix = 128 contiguous bytes): LBO 128 B between k halves, SBO 256 B.
+__device__ __forceinline__ uint64_t hn_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+    d |= uint64_t(128 >> 4) << 16;
+    d |= uint64_t(256 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    return d;
+}
+constexpr int HN_TILE_BYTES = TN * 16 * 2;   // 4 KB per 128-code tile
 // kind::f16 instruction descriptor: FP32 accumulator, FP16 A and B, both K-major, N=128, M=128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
 
@@ -194,21 +212,25 @@ __device__ __forceinline__ float key_to_t(uint32_t key, uint32_t top6) { return 
 
 // Best and runner-up of 64 keys.  Four independent (best, runner-up) chains over interleaved column pairs keep enough
 // independent work in flight to cover the ALU latency.  Per pair: 2 FADD + 2 IMAD (FMA pipe), 5 min/max (ALU pipe).
-template <bool HN_SMEM>
+// MODE 0: hn_off in global memory, 1: in shared memory, 2: folded into the accumulator by the MMA (no subtraction at all).
+template <int MODE>
 __device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float* hn_off, uint32_t key_mul,
                                        uint32_t& t1, uint32_t& t2) {
     uint32_t a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
     const float4* hn4 = reinterpret_cast<const float4*>(hn_off);
 #pragma unroll
     for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 h = HN_SMEM ? hn4[j4] : __ldg(hn4 + j4);
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 1) h = hn4[j4];
+        if (MODE == 0) h = __ldg(hn4 + j4);
         const float hh[4] = {h.x, h.y, h.z, h.w};
         uint32_t key[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = j4 * 4 + jj;
-            const float t = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) - hh[jj];
-            key[jj] = __float_as_uint(t) * key_mul + uint32_t(j);
+            const uint32_t acc = j < 32 ? v0[j & 31] : v1[j & 31];
+            const uint32_t tb = MODE == 2 ? acc : __float_as_uint(__uint_as_float(acc) - hh[jj]);
+            key[jj] = tb * key_mul + uint32_t(j);
         }
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -243,9 +265,10 @@ struct __align__(16) Smem {           // control block placed after the data sta
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
-    Cand cand[CD][2][TM];
-    float2 rowstat[CD][TM];           // (||x||^2, ||x - fp16(x)||^2) of the tiles waiting for their back stage
 };
+// after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
+// for their back stage); then either the folded -(||e||^2/2 - B) tiles or the FP32 offset vector.
+inline size_t handoff_bytes(int cd) { return size_t(cd) * (2 * TM * sizeof(Cand) + TM * sizeof(float2)); }
 
 // RESCORE = true additionally re-scores the shortlisted code in exact FP32 (needed for min_d / sum(min_d) and for
 // the audit output; it also halves the safety margin); RESCORE = false decides from the approximate scores alone.
@@ -258,7 +281,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     uint8_t* xs_base = smem;                                        // XS x 16 KB
     uint8_t* bs_base = smem + XS * X_STAGE_BYTES;                   // b_stages x 16 KB (1024-aligned)
     Smem* ctl = reinterpret_cast<Smem*>(bs_base + size_t(p.b_stages) * B_STAGE_BYTES);
-    float* hn_s = reinterpret_cast<float*>(ctl + 1);                // [Kp] when hn_in_smem
+    Cand* cand = reinterpret_cast<Cand*>(ctl + 1);                  // [cd][2][TM]
+    float2* rowstat = reinterpret_cast<float2*>(cand + size_t(p.cd) * 2 * TM);   // [cd][TM]
+    uint8_t* tail = reinterpret_cast<uint8_t*>(rowstat + size_t(p.cd) * TM);
+    float* hn_s = reinterpret_cast<float*>(tail);                   // [Kp] when hn_in_smem and not folded
+    uint8_t* hn_b = tail;                                           // [n_nt][4 KB] when folded
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float e_norm_max = __uint_as_float(p.hdr->e_norm_max_bits);
@@ -272,7 +299,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (p.hn_in_smem) {
+    // the folded offset must be representable as three FP16 terms; otherwise (absurdly large norms) every frame falls back
+    const bool fold_ok = ks.offset < 3.0e4f;
+    if (p.fold) {
+        // B.(1,1,1,0,...) = B - ||e||^2/2 split into hi + mid + lo FP16 terms (exact to ~2^-33 relative);
+        // padded codes (acc == 0) get t = 2^E, the smallest key of the range
+        for (int c = threadIdx.x; c < p.Kp; c += THREADS) {
+            const float val = c < p.K ? ks.offset - p.hn[c] : 2.f * ks.half_range;
+            const __half h1 = __float2half_rn(val);
+            const float r1 = val - __half2float(h1);
+            const __half h2 = __float2half_rn(r1);
+            const __half h3 = __float2half_rn(r1 - __half2float(h2));
+            const uint32_t w0 = uint32_t(__half_as_ushort(h1)) | (uint32_t(__half_as_ushort(h2)) << 16);
+            const uint32_t w1 = uint32_t(__half_as_ushort(h3));
+            uint4* dst = reinterpret_cast<uint4*>(hn_b + size_t(c >> 7) * HN_TILE_BYTES + size_t(((c & 127) >> 3) * 2) * 128 + size_t(c & 7) * 16);
+            dst[0] = make_uint4(w0, w1, 0u, 0u);          // k = 0..7  (core matrix of the first k half)
+            dst[8] = make_uint4(0u, 0u, 0u, 0u);          // k = 8..15 (second k half, +128 bytes)
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+    } else if (p.hn_in_smem) {
         // t = acc - (||e||^2/2 - B);  padded codes (acc == 0) get t = 2^E, the smallest key of the range
         for (int i = threadIdx.x; i < p.Kp; i += THREADS) hn_s[i] = i < p.K ? p.hn[i] - ks.offset : -2.f * ks.half_range;
     }
@@ -379,6 +424,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                         if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[bs])); ++qb; }
                     }
+                    if (p.fold && leader)   // one more k-step: [1,1,1,0..] x (B - ||e||^2/2 as hi+mid+lo) adds the offset in the tensor core
+                        tc_mma_ts(d_tmem, tmem + uint32_t(p.a_const_col), hn_desc(smem_u32(hn_b + size_t(nt) * HN_TILE_BYTES)), IDESC, 1u);
                     if (leader) tc_commit(smem_u32(&ctl->acc_full[s]));
                     VQ_TRACE_NT(11, it, nt);
                 }
@@ -393,16 +440,20 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const float e_err_max = __uint_as_float(p.hdr->e_err_max_bits);
         uint32_t qx = 0, it = 0;
         double sum_d = 0.0;
+        if (p.fold) {            // constant A slice [1, 1, 1, 0, ...] (FP16 pairs) for the folded k-step; ordered by the first a_full arrival
+            const uint32_t ones[8] = {0x3C003C00u, 0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tc_st8(tmem + lane_base + uint32_t(p.a_const_col), ones);
+        }
 
         // back stage of local tile j: merge the two scan groups, decide, write
         auto finish = [&](uint32_t j) {
             const int tile = first + int(j) * step;
-            const uint32_t cb = j % CD, cph = (j / CD) & 1;
+            const uint32_t cb = j % p.cd, cph = (j / p.cd) & 1;
             if (wq == 0) VQ_TRACE(6, j);
             mbar_wait<500>(smem_u32(&ctl->cand_full[cb]), cph);
             if (wq == 0) VQ_TRACE(7, j);
-            const Cand ca = ctl->cand[cb][0][r], cc = ctl->cand[cb][1][r];
-            const float2 st = ctl->rowstat[cb][r];
+            const Cand ca = cand[(cb * 2 + 0) * TM + r], cc = cand[(cb * 2 + 1) * TM + r];
+            const float2 st = rowstat[cb * TM + r];
             mbar_arrive_warp(smem_u32(&ctl->cand_empty[cb]));
             const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TM + r;
             const bool in_tile = t < p.T;
@@ -453,7 +504,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     // both approximate scores carry at most `err`; the difference of two t is exact
                     safe = (t_best - t_bound) > 2.f * err;
                 }
-                safe = safe && in_range && c1 < p.K;
+                safe = safe && in_range && c1 < p.K && (!p.fold || fold_ok);
 #if VQ_EXPERIMENT & 4                     /* timing experiment: never take the fallback */
                 safe = true;
 #endif
@@ -509,7 +560,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 mbar_arrive_warp(smem_u32(&ctl->x_empty[s]));                      // the stage's data now lives in registers
                 tc_st16(a_tmem + uint32_t(ch * (XCH / 2)), pk);
             }
-            ctl->rowstat[it % CD][r] = make_float2(xx, rr);                   // read back by this same thread in finish()
+            rowstat[(it % p.cd) * TM + r] = make_float2(xx, rr);                   // read back by this same thread in finish()
             tc_wait_st();
             tc_fence_before();
             mbar_arrive_warp(smem_u32(&ctl->a_full[a]));
@@ -559,8 +610,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
                     t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
 #else
-                    if (p.hn_in_smem) scan64<true>(v0, v1, hn_s + cbase, key_mul, t1, t2);
-                    else scan64<false>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
+                    if (p.fold) scan64<2>(v0, v1, nullptr, key_mul, t1, t2);
+                    else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, key_mul, t1, t2);
+                    else scan64<0>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
 #endif
                     // fold the pair of this half tile into the running pair
                     if (t1 > r1) {
@@ -573,10 +625,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 if (warp == 4) VQ_TRACE_NT(14, it, nt);
             }
-            const uint32_t cb = it % CD, cph = (it / CD) & 1;
+            const uint32_t cb = it % p.cd, cph = (it / p.cd) & 1;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
             Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1; c.pad = 0;
-            ctl->cand[cb][wg][r] = c;
+            cand[(cb * 2 + wg) * TM + r] = c;
             mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
             if (warp == 4) VQ_TRACE(9, it);
         }
@@ -644,12 +696,21 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     p.n_tiles = int(n_tiles);
     p.n_nt = w.Kp / TN; p.n_kb = w.Dp / BKB; p.n_xch = w.Dp / XCH;
     p.acc_stages = 2;                                           // one accumulator stage per scan group
-    p.a_bufs = std::min(A_BUFS_MAX, (512 - p.acc_stages * TN) / (w.Dp / 2));   // converted tiles that fit the remaining TMEM columns
-    p.lag = std::min(p.a_bufs, CD - 1);                         // the back stage trails the front stage by this many tiles
     p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
     p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
-    p.key_mul = 64u;
     p.hn_in_smem = w.Kp <= HN_SMEM_MAX ? 1 : 0;
+    // fold the per-code offset into the MMA when the codebook is resident and everything still fits shared memory
+    const size_t smem_base = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem);
+    p.fold = 0; p.cd = CD;
+    if (p.resident && smem_base + handoff_bytes(3) + size_t(p.n_nt) * HN_TILE_BYTES <= 227 * 1024) {
+        p.fold = 1;
+        p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES <= 227 * 1024 ? CD : 3;
+    }
+    p.a_const_col = 512 - 8;
+    const int a_cols = (p.fold ? p.a_const_col : 512) - p.acc_stages * TN;
+    p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
+    p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
+    p.key_mul = 64u;
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
 
     if (!p.hn_in_smem) {
@@ -678,8 +739,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(codebook) failed with CUresult %s%lld", "", (long long)r);
     }
-    const size_t smem = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem) +
-                        (p.hn_in_smem ? size_t(w.Kp) * 4 : 0);
+    const size_t smem = smem_base + handoff_bytes(p.cd) +
+                        (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES : (p.hn_in_smem ? size_t(w.Kp) * 4 : 0));
     VQ_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
