@@ -71,6 +71,7 @@ struct Params {
     int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, acc_stages, lag, resident, b_stages, vec_k;
     int hn_in_smem;
     int fold;                // -(||e||^2/2 - B) rides in the MMA as one extra k-step (resident codebooks only): no FADD, no loads in the scan
+    int pair;                // resident codebook with an even number of code tiles: MMAs are issued with N = 256
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
@@ -185,6 +186,7 @@ __device__ __forceinline__ uint64_t hn_desc(uint32_t smem_addr) {
 constexpr int HN_TILE_BYTES = TN * 16 * 2;   // 4 KB per 128-code tile
 // kind::f16 instruction descriptor: FP32 accumulator, FP16 A and B, both K-major, N=128, M=128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+constexpr uint32_t IDESC256 = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(256 >> 3) << 17) | (uint32_t(TM >> 4) << 24);   // N = 256
 
 // ------------------------------------------------------------------------------------------------ key arithmetic
 // Offset B = 1.5 * 2^E with 2^(E-1) >= 8 max||e||^2: every frame with ||x|| <= 7.4 max||e|| keeps its scores inside
@@ -359,7 +361,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         if (p.resident) {
             for (int nt = 0; nt < p.n_nt; ++nt)
                 for (int kb = 0; kb < p.n_kb; ++kb) {
-                    const int s = nt * p.n_kb + kb;
+                    const int s = kb * p.n_nt + nt;       // depth-block major: code tiles nt, nt+1 are adjacent (one N = 256 operand)
                     if (leader) {
                         mbar_expect_tx(smem_u32(&ctl->b_full[s]), B_STAGE_BYTES);
                         tma_load_2d(smem_u32(bs_base + size_t(s) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, nt * TN);
@@ -389,6 +391,36 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 tc_fence_after();
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
+                if (p.pair) {
+                    // Resident codebook, even number of code tiles: ONE tcgen05.mma with N = 256 fills both accumulator
+                    // stages (adjacent TMEM columns, adjacent B tiles) -- half the instructions, fences and barrier
+                    // round trips per frame tile of the N = 128 path below.
+                    for (int nt = 0; nt < p.n_nt; nt += 2, qa += 2) {
+                        const uint32_t sph = (qa >> 1) & 1u;
+                        mbar_wait<32>(smem_u32(&ctl->acc_empty[0]), sph ^ 1);
+                        mbar_wait<32>(smem_u32(&ctl->acc_empty[1]), sph ^ 1);
+                        tc_fence_after();
+                        VQ_TRACE_NT(10, it, nt);
+                        for (int kb = 0; kb < p.n_kb; ++kb) {
+                            const uint32_t bs = kb * p.n_nt + nt;
+                            if (it == 0) {
+                                mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
+                                mbar_wait<0>(smem_u32(&ctl->b_full[bs + 1]), 0);
+                                tc_fence_after();
+                            }
+                            const uint64_t bd = b_desc_base(smem_u32(bs_base + size_t(bs) * B_STAGE_BYTES));
+#pragma unroll
+                            for (int k4 = 0; k4 < BKB / 16; ++k4)
+                                if (leader)
+                                    tc_mma_ts(tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), bd + uint64_t(k4 * 2), IDESC256,
+                                              (kb | k4) != 0 ? 1u : 0u);
+                        }
+                        if (p.fold && leader)
+                            tc_mma_ts(tmem, tmem + uint32_t(p.a_const_col), hn_desc(smem_u32(hn_b + size_t(nt) * HN_TILE_BYTES)), IDESC256, 1u);
+                        if (leader) { tc_commit(smem_u32(&ctl->acc_full[0])); tc_commit(smem_u32(&ctl->acc_full[1])); }
+                        VQ_TRACE_NT(11, it, nt);
+                    }
+                } else
                 for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
                     const uint32_t s = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
                     mbar_wait<32>(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
@@ -398,7 +430,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     for (int kb = 0; kb < p.n_kb; ++kb) {
                         uint32_t bs;
                         if (p.resident) {
-                            bs = nt * p.n_kb + kb;
+                            bs = kb * p.n_nt + nt;
                             if (it == 0) mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
                         } else {
                             bs = qb % p.b_stages;
@@ -707,6 +739,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
         p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES <= 227 * 1024 ? CD : 3;
     }
     p.a_const_col = 512 - 8;
+    p.pair = (p.resident && p.n_nt % 2 == 0) ? 1 : 0;
     const int a_cols = (p.fold ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
