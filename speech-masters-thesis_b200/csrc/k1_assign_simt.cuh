@@ -14,13 +14,17 @@ constexpr int S_BN = 64;    // codes per inner tile
 constexpr int S_BK = 16;    // depth per step
 
 // LIST = false: tile i covers frames [t0, t0+128) of utterance n (tiles never straddle utterances).
-// LIST = true : tile i covers row_list[i*128 .. i*128+127]; the count lives in device memory.
+// LIST = true : tile i covers row_list[i*128 .. i*128+127]; the count lives in device memory.  The code range is split
+//               over blockIdx.y so that a short list still fills the machine; the partial (distance, index) minima
+//               meet in list_keys[] through a 64-bit atomicMin whose ordering is exactly "smaller distance, then lower
+//               index" (torch.min's tie rule), and assign_list_finish_kernel writes the results.
 template <bool LIST>
 __global__ void __launch_bounds__(256)
 assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
                    const float* __restrict__ k, const float* __restrict__ ee, int K,
                    int64_t* __restrict__ idx, float* __restrict__ min_d, double* __restrict__ scalars,
-                   const int* __restrict__ row_list, const int* __restrict__ row_count) {
+                   const int* __restrict__ row_list, const int* __restrict__ row_count,
+                   unsigned long long* __restrict__ list_keys) {
     __shared__ __align__(16) float Xs[S_BK][S_BM];
     __shared__ __align__(16) float Es[S_BK][S_BN + 4];
     __shared__ long long row_off[S_BM];      // offset of x[n, 0, t] for each tile row, -1 when out of range
@@ -33,7 +37,14 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
     const int64_t n_tiles = LIST ? (n_rows_list + S_BM - 1) / S_BM : N * tiles_per_utt;
     const bool vec_k = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
     double tile_sum = 0.0;
-    if (LIST && blockIdx.x == 0 && tid == 0 && scalars && n_rows_list) atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n_rows_list));
+    // codes [c_lo, c_hi) for this block (LIST mode: a 64-code-aligned slice per blockIdx.y)
+    int c_lo = 0, c_hi = K;
+    if (LIST) {
+        const int per = ((K + int(gridDim.y) - 1) / int(gridDim.y) + S_BN - 1) / S_BN * S_BN;
+        c_lo = min(K, int(blockIdx.y) * per);
+        c_hi = min(K, c_lo + per);
+        if (c_lo >= c_hi) return;
+    }
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
@@ -59,7 +70,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
         for (int i = 0; i < 8; ++i) { xx[i] = 0.f; bd[i] = __int_as_float(0x7f800000); bi[i] = 0x7fffffff; }
 
-        for (int c0 = 0; c0 < K; c0 += S_BN) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += S_BN) {
             float acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -106,7 +117,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
                     }
-                    if (c0 == 0) {
+                    if (c0 == c_lo) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) xx[i] = fmaf(a[i], a[i], xx[i]);
                     }
@@ -117,7 +128,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int c = c0 + tx * 4 + j;
-                if (c < K) {
+                if (c < c_hi) {
                     float e2 = ee[c];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -142,18 +153,54 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
             for (int i = 0; i < 8; ++i) {
                 int r = ty * 8 + i;
                 if (row_off[r] >= 0) {
-                    int64_t row;
-                    if (LIST) row = row_list[tile * S_BM + r];
-                    else row = (tile / tiles_per_utt) * T + (tile % tiles_per_utt) * S_BM + r;
-                    idx[row] = bi[i] == 0x7fffffff ? 0 : bi[i];
-                    if (min_d) min_d[row] = bd[i];
-                    tile_sum += double(bd[i]);
+                    if (LIST) {
+                        // orderable bits of the distance (monotone for all finite floats and +inf), then the index
+                        const unsigned b = __float_as_uint(bd[i]);
+                        const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                        const unsigned long long key = (static_cast<unsigned long long>(ord) << 32) | unsigned(bi[i]);
+                        atomicMin(&list_keys[tile * S_BM + r], key);
+                    } else {
+                        const int64_t row = (tile / tiles_per_utt) * T + (tile % tiles_per_utt) * S_BM + r;
+                        idx[row] = bi[i] == 0x7fffffff ? 0 : bi[i];
+                        if (min_d) min_d[row] = bd[i];
+                        tile_sum += double(bd[i]);
+                    }
                 }
             }
         }
     }
     double s = block_sum(tile_sum, red);
     if (tid == 0 && scalars && s != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], s);
+}
+
+}  // namespace vq
+
+namespace vq {
+
+// Writes the results of the split exact re-scan: one thread per listed row.
+__global__ void __launch_bounds__(256)
+assign_list_finish_kernel(const int* __restrict__ row_list, const int* __restrict__ row_count,
+                          const unsigned long long* __restrict__ list_keys, int64_t* __restrict__ idx,
+                          float* __restrict__ min_d, double* __restrict__ scalars) {
+    __shared__ double red[32];
+    const int n = *row_count;
+    double sum = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned long long key = list_keys[j];
+        const unsigned ord = unsigned(key >> 32);
+        const unsigned b = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
+        const float d = __uint_as_float(b);
+        const unsigned ci = unsigned(key & 0xffffffffu);
+        const int row = row_list[j];
+        idx[row] = ci == 0x7fffffffu ? 0 : int64_t(ci);
+        if (min_d) min_d[row] = d;
+        sum += double(d);
+    }
+    sum = block_sum(sum, red);
+    if (threadIdx.x == 0 && scalars) {
+        if (sum != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
+        if (blockIdx.x == 0 && n) atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n));
+    }
 }
 
 }  // namespace vq

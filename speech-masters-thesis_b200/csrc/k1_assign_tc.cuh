@@ -64,7 +64,7 @@ constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared m
 
 struct Params {
     const float* x; const float* k; const float* ee; const float* hn; const float* hn_off;
-    AssignHeader* hdr; int* unsafe_rows;
+    AssignHeader* hdr; int* unsafe_rows; unsigned long long* list_keys;
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
     int N, D, Dp, K, Kp, T;
@@ -556,7 +556,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&p.hdr->unsafe_count, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (unsafe) p.unsafe_rows[base + __popc(m & ((1u << lane) - 1u))] = int(row);
+                if (unsafe) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    p.unsafe_rows[pos] = int(row);
+                    p.list_keys[pos] = ~0ull;                    // identity of the re-scan's atomicMin
+                }
             }
         };
 
@@ -719,7 +723,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     EncodeTiledFn encode = encode_tiled_fn();
     VQ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is unavailable");
     Params p;
-    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows;
+    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.list_keys = w.list_keys;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.D = D; p.Dp = w.Dp; p.K = K; p.Kp = w.Kp; p.T = int(T);
     p.tiles_per_utt = int((T + TM - 1) / TM);

@@ -159,16 +159,21 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream, dbg, trace, trace_tiles,
                              trace ? (dbg != nullptr) : -1)) return 1;
         prof_mark(pslot, 2, stream);
-        // exact re-scan of the rows whose BF16 shortlist could not be proven safe (count lives on the device)
-        int grid = std::min<int64_t>(2 * num_sms(), (N * T + S_BM - 1) / S_BM);
-        assign_simt_kernel<true><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
-                                                           w.unsafe_rows, &w.hdr->unsafe_count);
+        // exact re-scan of the rows whose FP16 shortlist could not be proven safe (the count lives on the device):
+        // list tiles x code slices, so that a handful of rows still spreads over the machine
+        const int splits = std::max(1, std::min(16, (K + S_BN - 1) / S_BN));
+        const int gx = int(std::min<int64_t>(std::max(1, 4 * num_sms() / splits), (N * T + S_BM - 1) / S_BM));
+        assign_simt_kernel<true><<<dim3(gx, splits), 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
+                                                                     w.unsafe_rows, &w.hdr->unsafe_count, w.list_keys);
+        VQ_CUDA_OK(cudaGetLastError());
+        assign_list_finish_kernel<<<std::min(2 * num_sms(), 1024), 256, 0, stream>>>(w.unsafe_rows, &w.hdr->unsafe_count, w.list_keys,
+                                                                                   idx, min_d, scalars);
         VQ_CUDA_OK(cudaGetLastError());
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));
         assign_simt_kernel<false><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
-                                                            nullptr, nullptr);
+                                                            nullptr, nullptr, nullptr);
         VQ_CUDA_OK(cudaGetLastError());
         prof_mark(pslot, 2, stream);
     }
