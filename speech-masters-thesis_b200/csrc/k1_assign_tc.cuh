@@ -49,7 +49,7 @@ constexpr int XS = 4;                        // x stages
 constexpr int BKB = 64;                      // depth per codebook stage: 64 fp16 = 128 B = one swizzle row
 constexpr int X_STAGE_BYTES = XCH * TM * 4;  // 16 KB
 constexpr int B_STAGE_BYTES = TN * BKB * 2;  // 16 KB
-constexpr int B_RING = 6;                    // streaming ring depth
+constexpr int B_RING = 8;                    // streaming ring depth (4 pair stages when MMAs are issued with N = 256)
 constexpr int B_RESIDENT_MAX = 8;            // up to 8 stages (128 KB) stay resident
 constexpr int THREADS = 512;
 // Warp roles.  The scheduler favours the highest warp id of a sub-partition, so the single-lane issuers (TMA, MMA) sit
@@ -71,7 +71,7 @@ struct Params {
     int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, acc_stages, lag, resident, b_stages, vec_k;
     int hn_in_smem;
     int fold;                // -(||e||^2/2 - B) rides in the MMA as one extra k-step (resident codebooks only): no FADD, no loads in the scan
-    int pair;                // resident codebook with an even number of code tiles: MMAs are issued with N = 256
+    int pair;                // even number of code tiles: MMAs are issued with N = 256 over two adjacent B tiles
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
@@ -367,6 +367,21 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         tma_load_2d(smem_u32(bs_base + size_t(s) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, nt * TN);
                     }
                 }
+        } else if (p.pair) {
+            // streaming, N = 256 operands: a ring of PAIR stages (two adjacent 16 KB tiles: code tiles nt and nt+1 of one depth block)
+            const uint32_t n_ps = uint32_t(p.b_stages) >> 1;
+            uint32_t q = 0;
+            for (int tile = first; tile < p.n_tiles; tile += step)
+                for (int nt = 0; nt < p.n_nt; nt += 2)
+                    for (int kb = 0; kb < p.n_kb; ++kb, ++q) {
+                        const uint32_t s = q % n_ps, ph = (q / n_ps) & 1;
+                        mbar_wait<100>(smem_u32(&ctl->b_empty[s]), ph ^ 1);
+                        if (leader) {
+                            mbar_expect_tx(smem_u32(&ctl->b_full[s]), 2 * B_STAGE_BYTES);
+                            tma_load_2d(smem_u32(bs_base + size_t(2 * s) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, nt * TN);
+                            tma_load_2d(smem_u32(bs_base + size_t(2 * s + 1) * B_STAGE_BYTES), &b_map, smem_u32(&ctl->b_full[s]), kb * BKB, (nt + 1) * TN);
+                        }
+                    }
         } else {
             uint32_t q = 0;
             for (int tile = first; tile < p.n_tiles; tile += step)
@@ -392,7 +407,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
                 if (p.pair) {
-                    // Resident codebook, even number of code tiles: ONE tcgen05.mma with N = 256 fills both accumulator
+                    // Even number of code tiles: ONE tcgen05.mma with N = 256 fills both accumulator
                     // stages (adjacent TMEM columns, adjacent B tiles) -- half the instructions, fences and barrier
                     // round trips per frame tile of the N = 128 path below.
                     for (int nt = 0; nt < p.n_nt; nt += 2, qa += 2) {
@@ -402,11 +417,21 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         tc_fence_after();
                         VQ_TRACE_NT(10, it, nt);
                         for (int kb = 0; kb < p.n_kb; ++kb) {
-                            const uint32_t bs = kb * p.n_nt + nt;
-                            if (it == 0) {
-                                mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
-                                mbar_wait<0>(smem_u32(&ctl->b_full[bs + 1]), 0);
+                            uint32_t bs;                      // index of the first 16 KB tile of the N = 256 operand
+                            uint32_t ps = 0;
+                            if (p.resident) {
+                                bs = kb * p.n_nt + nt;
+                                if (it == 0) {
+                                    mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
+                                    mbar_wait<0>(smem_u32(&ctl->b_full[bs + 1]), 0);
+                                    tc_fence_after();
+                                }
+                            } else {
+                                const uint32_t n_ps = uint32_t(p.b_stages) >> 1;
+                                ps = qb % n_ps;
+                                mbar_wait<0>(smem_u32(&ctl->b_full[ps]), (qb / n_ps) & 1);
                                 tc_fence_after();
+                                bs = 2 * ps;
                             }
                             const uint64_t bd = b_desc_base(smem_u32(bs_base + size_t(bs) * B_STAGE_BYTES));
 #pragma unroll
@@ -414,6 +439,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                 if (leader)
                                     tc_mma_ts(tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), bd + uint64_t(k4 * 2), IDESC256,
                                               (kb | k4) != 0 ? 1u : 0u);
+                            if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[ps])); ++qb; }
                         }
                         if (p.fold && leader)
                             tc_mma_ts(tmem, tmem + uint32_t(p.a_const_col), hn_desc(smem_u32(hn_b + size_t(nt) * HN_TILE_BYTES)), IDESC256, 1u);
@@ -743,7 +769,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
         p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES <= 227 * 1024 ? CD : 3;
     }
     p.a_const_col = 512 - 8;
-    p.pair = (p.resident && p.n_nt % 2 == 0) ? 1 : 0;
+    p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     const int a_cols = (p.fold ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
