@@ -34,7 +34,11 @@ extern "C" {
 enum {
     VQ_ALGO_AUTO = 0,   /* tcgen05 path when the shape allows it, else the SIMT path                   */
     VQ_ALGO_SIMT = 1,   /* exact-FP32 register-tiled CUDA-core kernel (any shape)                      */
-    VQ_ALGO_TC   = 2    /* BF16 tcgen05/TMEM distance GEMM + top-2 + FP32 rescoring (+ exact fallback) */
+    VQ_ALGO_TC   = 2,   /* FP16 tcgen05/TMEM distance GEMM + (best, runner-up) scan + provable check (+ exact fallback) */
+    /* OR-able flag: the workspace already holds this codebook's prepared operands (FP16 image, norms) from an earlier
+     * vq_assign on the SAME workspace with the SAME k / k_bins / emb_width and unchanged codebook values: skip the
+     * per-call preparation.  What the generate_vq_dataset loop wants (frozen codebook, many batches). */
+    VQ_ALGO_PREPARED = 256
 };
 
 /* ---- scalar slots (fp64 accumulators in caller-owned device memory, VQ_NUM_SCALARS doubles) --- */

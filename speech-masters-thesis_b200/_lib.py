@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQB200_LIB", os.path.join(_HERE, "lib", "libvqb200.so"))   # override only for A/B experiments
 
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+ALGO_PREPARED = 256
 ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC}
 
 # scalar slots / result slots (mirror of the enums in include/vqb200.h)

@@ -6,6 +6,7 @@
 // (2) LIST mode: the exact re-scan of the few rows the tcgen05 kernel flags as unsafe.
 #pragma once
 #include "vq_common.cuh"
+#include "k1_prepare.cuh"
 
 namespace vq {
 
@@ -17,13 +18,13 @@ constexpr int S_BK = 16;    // depth per step
 // LIST = true : tile i covers row_list[i*128 .. i*128+127]; the count lives in device memory.  The code range is split
 //               over blockIdx.y so that a short list still fills the machine; the partial (distance, index) minima
 //               meet in list_keys[] through a 64-bit atomicMin whose ordering is exactly "smaller distance, then lower
-//               index" (torch.min's tie rule), and assign_list_finish_kernel writes the results.
+//               index" (torch.min's tie rule); the last block to finish writes the results.
 template <bool LIST>
 __global__ void __launch_bounds__(256)
 assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
                    const float* __restrict__ k, const float* __restrict__ ee, int K,
                    int64_t* __restrict__ idx, float* __restrict__ min_d, double* __restrict__ scalars,
-                   const int* __restrict__ row_list, const int* __restrict__ row_count,
+                   const int* __restrict__ row_list, AssignHeader* __restrict__ hdr,
                    unsigned long long* __restrict__ list_keys) {
     __shared__ __align__(16) float Xs[S_BK][S_BM];
     __shared__ __align__(16) float Es[S_BK][S_BN + 4];
@@ -33,7 +34,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t tiles_per_utt = (T + S_BM - 1) / S_BM;
-    const int64_t n_rows_list = LIST ? int64_t(*row_count) : 0;
+    const int64_t n_rows_list = LIST ? int64_t(*reinterpret_cast<volatile int*>(&hdr->unsafe_count)) : 0;
     const int64_t n_tiles = LIST ? (n_rows_list + S_BM - 1) / S_BM : N * tiles_per_utt;
     const bool vec_k = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
     double tile_sum = 0.0;
@@ -42,11 +43,10 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
     if (LIST) {
         const int per = ((K + int(gridDim.y) - 1) / int(gridDim.y) + S_BN - 1) / S_BN * S_BN;
         c_lo = min(K, int(blockIdx.y) * per);
-        c_hi = min(K, c_lo + per);
-        if (c_lo >= c_hi) return;
+        c_hi = min(K, c_lo + per);            // empty slices skip the tile loop but still take a ticket below
     }
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles && c_lo < c_hi; tile += gridDim.x) {
         __syncthreads();
         if (tid < S_BM) {
             long long off = -1;
@@ -169,38 +169,44 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
             }
         }
     }
+    if (LIST) {
+        if (n_rows_list == 0) return;         // common case (speech-like latents): nothing to do, nothing to re-arm
+        // the last block to finish writes the results of the whole list (one thread per listed row) and re-arms the header
+        __shared__ bool is_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned ticket = atomicAdd(&hdr->list_ticket, 1u);
+            is_last = ticket == gridDim.x * gridDim.y - 1;
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        double sum = 0.0;
+        for (int64_t j = tid; j < n_rows_list; j += blockDim.x) {
+            const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&list_keys[j]);
+            const unsigned ord = unsigned(key >> 32);
+            const unsigned b = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
+            const float d = __uint_as_float(b);
+            const unsigned ci = unsigned(key & 0xffffffffu);
+            const int row = row_list[j];
+            idx[row] = ci == 0x7fffffffu ? 0 : int64_t(ci);
+            if (min_d) min_d[row] = d;
+            sum += double(d);
+        }
+        sum = block_sum(sum, red);
+        if (tid == 0) {
+            if (scalars && n_rows_list) {
+                atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
+                atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n_rows_list));
+            }
+            hdr->unsafe_count = 0;            // ready for the next vq_assign on this workspace (no memset needed)
+            hdr->list_ticket = 0;
+        }
+        return;
+    }
     double s = block_sum(tile_sum, red);
     if (tid == 0 && scalars && s != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], s);
-}
-
-}  // namespace vq
-
-namespace vq {
-
-// Writes the results of the split exact re-scan: one thread per listed row.
-__global__ void __launch_bounds__(256)
-assign_list_finish_kernel(const int* __restrict__ row_list, const int* __restrict__ row_count,
-                          const unsigned long long* __restrict__ list_keys, int64_t* __restrict__ idx,
-                          float* __restrict__ min_d, double* __restrict__ scalars) {
-    __shared__ double red[32];
-    const int n = *row_count;
-    double sum = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const unsigned long long key = list_keys[j];
-        const unsigned ord = unsigned(key >> 32);
-        const unsigned b = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
-        const float d = __uint_as_float(b);
-        const unsigned ci = unsigned(key & 0xffffffffu);
-        const int row = row_list[j];
-        idx[row] = ci == 0x7fffffffu ? 0 : int64_t(ci);
-        if (min_d) min_d[row] = d;
-        sum += double(d);
-    }
-    sum = block_sum(sum, red);
-    if (threadIdx.x == 0 && scalars) {
-        if (sum != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
-        if (blockIdx.x == 0 && n) atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n));
-    }
 }
 
 }  // namespace vq

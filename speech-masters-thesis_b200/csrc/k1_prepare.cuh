@@ -11,8 +11,9 @@ namespace vq {
 struct AssignHeader {
     unsigned int e_norm_max_bits;   // max_c ||fp16(e_c)||            (float bits; non-negative => uint order == float order)
     unsigned int e_err_max_bits;    // max_c ||e_c - fp16(e_c)||
-    int unsafe_count;               // rows queued for the exact fallback
-    int pad[61];
+    int unsafe_count;               // rows queued for the exact fallback (reset by the fallback kernel's last block)
+    unsigned int list_ticket;       // last-block ticket of the fallback kernel
+    int pad[60];
 };
 static_assert(sizeof(AssignHeader) == 256, "header is 256 bytes");
 

@@ -134,6 +134,8 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
     AssignWorkspace w = carve_workspace(workspace, N * T, K, int(D));
     VQ_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see vq_workspace_bytes)");
 
+    const bool prepared = (algo & VQ_ALGO_PREPARED) != 0;
+    algo &= ~VQ_ALGO_PREPARED;
     bool use_tc = false;
     if (algo == VQ_ALGO_TC) {
         const char* why = tc_unsupported_reason(x, N, int(D), T, K);
@@ -145,13 +147,13 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         VQ_REQUIRE(algo == VQ_ALGO_SIMT, "unknown algo");
     }
 
-    VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
     const int pslot = (g_prof.on && g_prof.n < PROF_RING) ? g_prof.n++ : -1;
     prof_mark(pslot, 0, stream);
-    {
+    if (!prepared) {
+        VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
         int blocks = (w.Kp * 32 + 255) / 256;
         codebook_prepare_kernel<<<blocks, 256, 0, stream>>>(k, K, int(D), w.Kp, w.Dp, w.ee, w.hn,
-                                                            use_tc ? w.eb : nullptr, w.hdr);
+                                                            w.eb, w.hdr);
         VQ_CUDA_OK(cudaGetLastError());
     }
     prof_mark(pslot, 1, stream);
@@ -164,10 +166,7 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         const int splits = std::max(1, std::min(16, (K + S_BN - 1) / S_BN));
         const int gx = int(std::min<int64_t>(std::max(1, 4 * num_sms() / splits), (N * T + S_BM - 1) / S_BM));
         assign_simt_kernel<true><<<dim3(gx, splits), 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
-                                                                     w.unsafe_rows, &w.hdr->unsafe_count, w.list_keys);
-        VQ_CUDA_OK(cudaGetLastError());
-        assign_list_finish_kernel<<<std::min(2 * num_sms(), 1024), 256, 0, stream>>>(w.unsafe_rows, &w.hdr->unsafe_count, w.list_keys,
-                                                                                   idx, min_d, scalars);
+                                                                     w.unsafe_rows, w.hdr, w.list_keys);
         VQ_CUDA_OK(cudaGetLastError());
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
@@ -315,6 +314,7 @@ struct vq_host_ctx {
     int64_t* h_idx = nullptr;
     double* h_scalars = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
+    bool prepared[2] = {false, false};      // workspace b already holds the current codebook's operands
 };
 
 void vq_host_ctx_destroy(vq_host_ctx* c) {
@@ -367,6 +367,7 @@ int vq_host_ctx_set_codebook(vq_host_ctx* c, const float* k_host) {
     VQ_REQUIRE(c && k_host, "null pointer");
     VQ_CUDA_OK(cudaSetDevice(c->device));
     VQ_CUDA_OK(cudaMemcpy(c->d_k, k_host, size_t(c->K) * c->D * 4, cudaMemcpyHostToDevice));
+    c->prepared[0] = c->prepared[1] = false;
     return 0;
 }
 
@@ -397,8 +398,9 @@ int vq_encode_host(vq_host_ctx* c, const float* x_host, int64_t N, int64_t T, in
         cudaMemcpyAsync(c->d_x[b], x_host + n0 * int64_t(c->D) * T, size_t(nn) * bytes_per_utt, cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(c->d_scalars[b], 0, VQ_NUM_SCALARS * 8, s);
         rc = vq_assign(c->d_x[b], nn, c->D, T, c->d_k, c->K, c->d_idx[b], nullptr, c->d_scalars[b], c->d_ws[b],
-                       c->ws_bytes, VQ_ALGO_AUTO, s);
+                       c->ws_bytes, VQ_ALGO_AUTO | (c->prepared[b] ? VQ_ALGO_PREPARED : 0), s);
         if (rc) break;
+        c->prepared[b] = true;
         cudaMemcpyAsync(idx_host + n0 * T, c->d_idx[b], size_t(nn) * T * 8, cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(c->h_scalars + b * VQ_NUM_SCALARS, c->d_scalars[b], VQ_NUM_SCALARS * 8, cudaMemcpyDeviceToHost, s);
         cudaEventRecord(done[b], s);

@@ -36,8 +36,10 @@ def _require_cuda(t, what):
 
 
 class _Workspace:
-    """Per-device scratch for K1 (BF16 codebook image, norms, fallback worklist); grows on demand."""
+    """Per-device scratch for K1 (FP16 codebook image, norms, fallback worklist); grows on demand.  Remembers which
+    codebook it was last prepared for, so a frozen codebook (the generate_vq_dataset loop) is prepared once."""
     _cache = {}
+    _prepared = {}
 
     @classmethod
     def get(cls, device, n, t, k, d):
@@ -48,7 +50,28 @@ class _Workspace:
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
             cls._cache[key] = buf
+            cls._prepared.pop(key, None)
         return buf
+
+    _counter = 0
+
+    @classmethod
+    def prepared_flag(cls, device, ws, k):
+        """ALGO_PREPARED when `ws` still holds the operands of this very tensor OBJECT at its current version.
+
+        The tag lives on the tensor object (an address can be recycled by the caching allocator, an object cannot be
+        confused with its successor) and is matched against the token of the last preparation done in `ws`."""
+        key = (device.type, device.index)
+        tag = getattr(k, "_vqb200_prepared", None)
+        if tag is not None and tag == (cls._prepared.get(key), ws.data_ptr(), k._version):
+            return _lib.ALGO_PREPARED
+        cls._counter += 1
+        cls._prepared[key] = cls._counter
+        try:
+            k._vqb200_prepared = (cls._counter, ws.data_ptr(), k._version)
+        except AttributeError:
+            pass
+        return 0
 
 
 # --------------------------------------------------------------------------------------- raw ops
@@ -63,9 +86,10 @@ def assign(x, k, algo="auto", want_min_d=False, scalars=None):
     if n * t == 0:
         return idx, min_d
     ws = _Workspace.get(x.device, n, t, kk, d)
+    flag = _Workspace.prepared_flag(x.device, ws, k)
     with torch.cuda.device(x.device):
         check(lib.vq_assign(ptr(x), n, d, t, ptr(k), kk, ptr(idx), ptr(min_d), ptr(scalars), ptr(ws), ws.numel(),
-                            _lib.ALGOS[algo], _stream(x)), "vq_assign")
+                            _lib.ALGOS[algo] | flag, _stream(x)), "vq_assign")
     return idx, min_d
 
 

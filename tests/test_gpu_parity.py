@@ -374,3 +374,42 @@ def test_raw_abi_error_behaviour_and_host_path(vq):
         assert lib.vq_encode_host(ctx, xh.ctypes.data, n + 1, t, out.ctypes.data, None) != 0     # larger than the context
     finally:
         lib.vq_host_ctx_destroy(ctx)
+
+
+def test_prepared_codebook_cache_follows_the_codebook(vq):
+    """The module prepares a frozen codebook once (VQ_ALGO_PREPARED afterwards); in-place edits, a new tensor object or a
+    second module sharing the workspace must all trigger a fresh preparation."""
+    gen = torch.Generator().manual_seed(21)
+    K, D = 256, 64
+    x = torch.randn(3, D, 128, generator=gen)
+    mask = torch.ones(3, 1, 128)
+    rows, _, _ = O.flatten_nct(x, mask)
+    xd, md = x.to(DEV), mask.to(DEV)
+
+    def oracle_idx(code):
+        return O.assign(rows, code)[0]
+
+    a = vq.BottleneckBlock(K, D, 0.99, 1.0).to(DEV)
+    code_a = torch.randn(K, D, generator=gen)
+    a.k = code_a.to(DEV)
+    for _ in range(3):                                   # 2nd and 3rd call reuse the prepared operands
+        check_indices(rows, code_a, oracle_idx(code_a), a.encode(xd, md))
+    a.k.mul_(-1.0)                                       # in-place edit: version counter moves
+    check_indices(rows, -code_a, oracle_idx(-code_a), a.encode(xd, md))
+    b = vq.BottleneckBlock(K, D, 0.99, 1.0).to(DEV)      # another module, same device workspace
+    code_b = torch.randn(K, D, generator=gen)
+    b.k = code_b.to(DEV)
+    check_indices(rows, code_b, oracle_idx(code_b), b.encode(xd, md))
+    check_indices(rows, -code_a, oracle_idx(-code_a), a.encode(xd, md))     # a's tag is stale now: prepared again
+    a.k = code_b.to(DEV) * 0.5                           # rebinding: a new tensor object
+    check_indices(rows, code_b * 0.5, oracle_idx(code_b * 0.5), a.encode(xd, md))
+    # raw ABI: the flag on a prepared workspace gives the same indices as a full call
+    lib = vq._lib.load()
+    kd = (code_b * 0.5).to(DEV)
+    ws = torch.empty(int(lib.vq_workspace_bytes(3, 128, K, D)), dtype=torch.uint8, device=DEV)
+    i0 = torch.empty(3, 128, dtype=torch.int64, device=DEV)
+    i1 = torch.empty_like(i0)
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.vq_assign(xd.data_ptr(), 3, D, 128, kd.data_ptr(), K, i0.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 0, s) == 0
+    assert lib.vq_assign(xd.data_ptr(), 3, D, 128, kd.data_ptr(), K, i1.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 256, s) == 0
+    assert torch.equal(i0, i1)
