@@ -161,7 +161,7 @@ class BottleneckBlock(nn.Module):
     """Drop-in for ``BottleneckBlock`` (bottleneck.py:10-201)."""
 
     def __init__(self, k_bins: int, emb_width: int, mu: float, threshold: float, laplace_eps: float = 0.0,
-                 algo: str = "auto"):
+                 algo: str = "auto", rng_parity: bool = True):
         super().__init__()
         self.k_bins = k_bins
         self.emb_width = emb_width
@@ -169,6 +169,10 @@ class BottleneckBlock(nn.Module):
         self.threshold = threshold
         self.laplace_eps = laplace_eps        # 0.0 == the reference (it has no Laplace smoothing)
         self.algo = algo
+        # True: restart rows replay the reference's RNG calls (CPU randperm over all valid rows: one host sync and ~2 ms of
+        # host time at 300 k frames).  False: K rows are drawn on the device (with replacement, no sync); same distribution,
+        # different random stream.
+        self.rng_parity = rng_parity
         self.reset_k()
 
     # ---- state (bottleneck.py:20-24)
@@ -194,6 +198,17 @@ class BottleneckBlock(nn.Module):
         but gathering K rows instead of permuting the whole batch."""
         n, d, t = x.shape
         flat = mask.reshape(-1) if mask is not None else None
+        if not self.rng_parity:
+            # device-only: the r-th valid frame for K uniform ranks r, via a prefix sum of the mask (no host sync)
+            valid = (flat != 0) if flat is not None else torch.ones(n * t, dtype=torch.bool, device=x.device)
+            csum = torch.cumsum(valid, 0)
+            m = csum[-1]
+            ranks = (torch.rand(self.k_bins, device=x.device) * m).long().clamp_(min=0)
+            ranks = torch.minimum(ranks, (m - 1).clamp_(min=0))
+            pos = torch.searchsorted(csum, ranks + 1).clamp_(max=n * t - 1)
+            rows = gather_rows(x, pos)
+            jitter = (m < self.k_bins).to(rows.dtype) * (0.01 / math.sqrt(d))      # the reference's _tile noise, only when rows repeat
+            return rows + torch.randn_like(rows) * jitter
         valid_pos = (torch.nonzero(flat != 0)[:, 0] if flat is not None
                      else torch.arange(n * t, device=x.device))          # host sync (the reference has three)
         m = valid_pos.numel()

@@ -413,3 +413,31 @@ def test_prepared_codebook_cache_follows_the_codebook(vq):
     assert lib.vq_assign(xd.data_ptr(), 3, D, 128, kd.data_ptr(), K, i0.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 0, s) == 0
     assert lib.vq_assign(xd.data_ptr(), 3, D, 128, kd.data_ptr(), K, i1.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 256, s) == 0
     assert torch.equal(i0, i1)
+
+
+def test_device_side_restart_rows(vq):
+    """rng_parity=False: no host sync; restart rows are valid batch rows (or jittered copies when there are too few),
+    everything that does not depend on the random stream still matches the oracle."""
+    gen = torch.Generator().manual_seed(33)
+    K, D = 64, 16
+    code = torch.randn(K, D, generator=gen)
+    lengths = torch.tensor([120, 77, 10])
+    x, mask = O.synthetic_batch(lengths, D, gen, codebook=code)
+    rows, _, valid = O.flatten_nct(x, mask)
+    blk = vq.BottleneckBlock(K, D, 0.99, 50.0, rng_parity=False).to(DEV)        # threshold 50: every code is re-seeded
+    blk.k, blk.k_sum, blk.k_elem, blk.init = code.to(DEV), code.to(DEV).clone(), torch.ones(K, device=DEV), True
+    blk.train()
+    x_l, x_q, commit, metrics = blk(x.to(DEV), mask.to(DEV))
+    st = O.CodebookState(K, D, 0.99, 50.0, code.clone(), code.clone(), torch.ones(K), True)
+    o_l, o_q, o_commit, o_m = O.forward(st, x, mask, update_k=True, k_rand=torch.zeros(K, D))
+    check_indices(rows, code, o_l, x_l)
+    close(commit, o_commit)
+    close(blk.k_sum, st.k_sum, rtol=1e-5, atol=1e-5)
+    assert float(metrics["usage"]) == 0.0
+    dmin = (blk.k.cpu()[:, None, :] - rows[valid][None, :, :]).abs().amax(dim=2).min(dim=1).values
+    assert float(dmin.max()) == 0.0                                             # every new code IS a valid batch row
+    fresh = vq.BottleneckBlock(K, D, 0.99, 1.0, rng_parity=False).to(DEV)       # init path with fewer rows than codes
+    fresh.train()
+    tiny_x, tiny_m = x[:, :, :8].contiguous(), mask[:, :, :8].contiguous()
+    fresh(tiny_x.to(DEV), tiny_m.to(DEV))
+    assert fresh.init and fresh.k.shape == (K, D) and bool(torch.isfinite(fresh.k).all())
