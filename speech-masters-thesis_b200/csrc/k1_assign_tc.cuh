@@ -103,6 +103,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // SLEEP_NS > 0 backs off with nanosleep between probes (used where a few hundred ns of wake-up latency is harmless).
+constexpr int REGS_ISSUER = 40, REGS_FRONT = 104, REGS_SCAN = 184;    // 4*40 + 4*104 + 8*184 = 2048 = 16 warps x 128
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -111,6 +115,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
         if (++spins > SPIN_LIMIT) __trap();
     } while (!mbar_try_wait(bar, parity));
+}
+// Critical-path waits (accumulator full / empty): mbarrier.test_wait never suspends the warp, so the waiter resumes a few
+// cycles after the phase flips; the suspending try_wait above was measured to resume 150-600 cycles late.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (++spins > (SPIN_LIMIT << 6)) __trap();
+    } while (!ok);
 }
 // One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
 // asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
@@ -212,40 +226,96 @@ __device__ __forceinline__ KeySpace make_key_space(float e_norm_max) {
 }
 __device__ __forceinline__ float key_to_t(uint32_t key, uint32_t top6) { return __uint_as_float((key >> 6) | top6); }
 
-// Best and runner-up of 64 keys.  Four independent (best, runner-up) chains over interleaved column pairs keep enough
-// independent work in flight to cover the ALU latency.  Per pair: 2 FADD + 2 IMAD (FMA pipe), 5 min/max (ALU pipe).
+// Best and runner-up of 64 keys in ~1.2 integer min/max per code (the ALU pipe is what bounds this kernel at small D).
+// Every column belongs to two families of running maxima: its RESIDUE chain (column mod 16, ch[16], kept over all the
+// code tiles a scan group visits) and its BLOCK (16 consecutive columns).  A (residue, block) cell holds exactly one
+// column, so any code other than the winner differs from it in residue or in block, and
+//     runner-up = max( best block maximum outside the winner's block , best residue chain outside the winner's chain )
+// exactly.  Maxima cost one 3-input max per two codes and family; the per-code (min, max, min, max3, max) top-2 update of
+// a direct scan is only paid per block (here, t1/t2 = top-2 over the four block maxima) and once per frame for the chains.
 // MODE 0: hn_off in global memory, 1: in shared memory, 2: folded into the accumulator by the MMA (no subtraction at all).
 template <int MODE>
 __device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float* hn_off, uint32_t key_mul,
-                                       uint32_t& t1, uint32_t& t2) {
-    uint32_t a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
+                                       uint32_t (&ch)[16], uint32_t& t1, uint32_t& t2) {
     const float4* hn4 = reinterpret_cast<const float4*>(hn_off);
+    uint32_t key[64];
 #pragma unroll
     for (int j4 = 0; j4 < 16; ++j4) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == 1) h = hn4[j4];
         if (MODE == 0) h = __ldg(hn4 + j4);
         const float hh[4] = {h.x, h.y, h.z, h.w};
-        uint32_t key[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = j4 * 4 + jj;
             const uint32_t acc = j < 32 ? v0[j & 31] : v1[j & 31];
             const uint32_t tb = MODE == 2 ? acc : __float_as_uint(__uint_as_float(acc) - hh[jj]);
-            key[jj] = tb * key_mul + uint32_t(j);
+            key[j] = tb * key_mul + uint32_t(j);
         }
+    }
+    uint32_t bm[4];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int g = (j4 * 2 + h2) & 3;
-            const uint32_t hi = max(key[2 * h2], key[2 * h2 + 1]), lo = min(key[2 * h2], key[2 * h2 + 1]);
-            a2[g] = __vimax3_u32(a2[g], min(a1[g], hi), lo);
-            a1[g] = max(a1[g], hi);
-        }
+    for (int b = 0; b < 4; ++b) {                        // block b = columns [16b, 16b + 16)
+        const uint32_t* k = key + 16 * b;
+        uint32_t m = __vimax3_u32(k[0], k[1], k[2]);
+        m = __vimax3_u32(m, k[3], k[4]);
+        m = __vimax3_u32(m, k[5], k[6]);
+        m = __vimax3_u32(m, k[7], k[8]);
+        m = __vimax3_u32(m, k[9], k[10]);
+        m = __vimax3_u32(m, k[11], k[12]);
+        m = __vimax3_u32(m, k[13], k[14]);
+        bm[b] = max(m, k[15]);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {                       // residue r = columns r, r + 16, r + 32, r + 48
+        ch[r] = __vimax3_u32(ch[r], key[r], key[r + 16]);
+        ch[r] = __vimax3_u32(ch[r], key[r + 32], key[r + 48]);
+    }
+    const uint32_t m01 = max(bm[0], bm[1]), n01 = min(bm[0], bm[1]), m23 = max(bm[2], bm[3]), n23 = min(bm[2], bm[3]);
+    t1 = max(m01, m23);
+    t2 = __vimax3_u32(min(m01, m23), n01, n23);
+}
+// Largest value of ch[] outside the chain that holds the overall maximum (= second largest of the 16 chain maxima).
+__device__ __forceinline__ uint32_t chains_runner_up(const uint32_t (&ch)[16]) {
+    uint32_t a1[4], a2[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t h0 = max(ch[4 * g], ch[4 * g + 1]), l0 = min(ch[4 * g], ch[4 * g + 1]);
+        const uint32_t h1 = max(ch[4 * g + 2], ch[4 * g + 3]), l1 = min(ch[4 * g + 2], ch[4 * g + 3]);
+        a1[g] = max(h0, h1);
+        a2[g] = __vimax3_u32(min(h0, h1), l0, l1);
     }
     const uint32_t b1 = max(a1[0], a1[1]), b2 = __vimax3_u32(min(a1[0], a1[1]), a2[0], a2[1]);
     const uint32_t c1 = max(a1[2], a1[3]), c2 = __vimax3_u32(min(a1[2], a1[3]), a2[2], a2[3]);
-    t1 = max(b1, c1);
-    t2 = __vimax3_u32(min(b1, c1), b2, c2);
+    return __vimax3_u32(min(b1, c1), b2, c2);
+}
+
+// One accumulator tile's worth of MMAs as straight-line code (the tensor core's queue is only a couple of instructions deep,
+// so every branch / constant load between two tcgen05.mma of a batch is a bubble in the tensor pipe).
+// b: descriptor of the (k block 0) B tile, kb_stride: descriptor distance between k blocks, a_tmem: TMEM column of depth 0.
+template <int NKB, uint32_t IDESC_>
+__device__ __forceinline__ void issue_batch(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint64_t kb_stride) {
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+        for (int k4 = 0; k4 < BKB / 16; ++k4)
+            tc_mma_ts(d_tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), b + uint64_t(kb) * kb_stride + uint64_t(k4 * 2), IDESC_,
+                      (kb | k4) != 0 ? 1u : 0u);
+}
+template <uint32_t IDESC_>
+__device__ __forceinline__ void issue_batch_n(int n_kb, uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint64_t kb_stride) {
+    switch (n_kb) {
+        case 1: issue_batch<1, IDESC_>(d_tmem, a_tmem, b, kb_stride); break;
+        case 2: issue_batch<2, IDESC_>(d_tmem, a_tmem, b, kb_stride); break;
+        case 4: issue_batch<4, IDESC_>(d_tmem, a_tmem, b, kb_stride); break;
+        case 8: issue_batch<8, IDESC_>(d_tmem, a_tmem, b, kb_stride); break;
+        default:
+            for (int kb = 0; kb < n_kb; ++kb)
+#pragma unroll
+                for (int k4 = 0; k4 < BKB / 16; ++k4)
+                    tc_mma_ts(d_tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), b + uint64_t(kb) * kb_stride + uint64_t(k4 * 2), IDESC_,
+                              (kb | k4) != 0 ? 1u : 0u);
+    }
 }
 
 // timeline probe: event e of local tile `it` of CTA 0
@@ -335,8 +405,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 
     const int first = blockIdx.x, step = gridDim.x;
 
+    // Register file re-split (the CTA owns all 64 K registers at 128 per thread): the four issuer warps and the front
+    // group give registers to the scan groups, which then hold a whole 128-column accumulator stage in registers and
+    // hand the stage back to the tensor core BEFORE scanning it (the MMA of the next code tiles overlaps the scan).
+
     if (warp == W_XPROD) {
         // ============================================================ x producer
+        reg_dec<REGS_ISSUER>();
         const bool leader = elect_one();
         uint32_t q = 0;
         for (int tile = first; tile < p.n_tiles; tile += step) {
@@ -357,6 +432,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         }
     } else if (warp == W_BPROD) {
         // ============================================================ codebook producer
+        reg_dec<REGS_ISSUER>();
         const bool leader = elect_one();
         if (p.resident) {
             for (int nt = 0; nt < p.n_nt; ++nt)
@@ -397,6 +473,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         }
     } else if (warp == W_MMA) {
         // ============================================================ MMA issuer
+        reg_dec<REGS_ISSUER>();
         {
             const bool leader = elect_one();
             uint32_t qa = 0, qb = 0, it = 0;
@@ -406,6 +483,60 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 tc_fence_after();
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
+#if !(VQ_EXPERIMENT & (16 | 64 | 128))
+                if (p.resident && it != 0) {
+                    // Steady state with the codebook resident in shared memory (every B tile is known to have landed after
+                    // the first frame tile): nothing but barrier waits between straight-line MMA batches.
+                    const uint64_t bd0 = b_desc_base(smem_u32(bs_base));
+                    const uint64_t kb_stride = uint64_t(p.n_nt) * uint64_t(B_STAGE_BYTES >> 4);
+                    const uint64_t hd0 = hn_desc(smem_u32(hn_b));
+                    const uint32_t a_const = tmem + uint32_t(p.a_const_col);
+                    const int n_kb = p.n_kb, n_nt = p.n_nt;
+                    const bool fold = p.fold != 0;
+                    if (p.pair) {
+                        for (int nt = 0; nt < n_nt; nt += 2, qa += 2) {
+                            const uint32_t sph = (qa >> 1) & 1u;
+                            mbar_spin(smem_u32(&ctl->acc_empty[0]), sph ^ 1);
+                            mbar_spin(smem_u32(&ctl->acc_empty[1]), sph ^ 1);
+                            tc_fence_after();
+                            VQ_TRACE_NT(10, it, nt);
+                            if (leader) {
+                                issue_batch_n<IDESC256>(n_kb, tmem, a_tmem, bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4), kb_stride);
+                                if (fold) tc_mma_ts(tmem, a_const, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC256, 1u);
+                                tc_commit(smem_u32(&ctl->acc_full[0]));
+                                tc_commit(smem_u32(&ctl->acc_full[1]));
+                            }
+                            __syncwarp();
+                            VQ_TRACE_NT(11, it, nt);
+                            if (p.trace && p.trace_tiles >= 32) {       // probe only: when does the ISSUER see the batch complete?
+                                mbar_spin(smem_u32(&ctl->acc_full[0]), sph);
+                                VQ_TRACE_NT(15, it, nt);
+                            }
+                        }
+                    } else {
+                        for (int nt = 0; nt < n_nt; ++nt, ++qa) {
+                            const uint32_t st = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
+                            mbar_spin(smem_u32(&ctl->acc_empty[st]), sph ^ 1);
+                            tc_fence_after();
+                            VQ_TRACE_NT(10, it, nt);
+                            if (leader) {
+                                issue_batch_n<IDESC>(n_kb, tmem + st * TN, a_tmem, bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4), kb_stride);
+                                if (fold) tc_mma_ts(tmem + st * TN, a_const, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
+                                tc_commit(smem_u32(&ctl->acc_full[st]));
+                            }
+                            __syncwarp();
+                            VQ_TRACE_NT(11, it, nt);
+                            if (p.trace && p.trace_tiles >= 32) {       // probe only: when does the ISSUER see the batch complete?
+                                mbar_spin(smem_u32(&ctl->acc_full[st]), sph);
+                                VQ_TRACE_NT(15, it, nt);
+                            }
+                        }
+                    }
+                    if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
+                    VQ_TRACE(2, it);
+                    continue;
+                }
+#endif
                 if (p.pair) {
                     // Even number of code tiles: ONE tcgen05.mma with N = 256 fills both accumulator
                     // stages (adjacent TMEM columns, adjacent B tiles) -- half the instructions, fences and barrier
@@ -493,6 +624,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         }
     } else if (warp < 4) {
         // ============================================================ front/back group (thread == frame)
+        reg_dec<REGS_FRONT>();
         const int wq = warp & 3, r = wq * 32 + lane;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
         const float e_err_max = __uint_as_float(p.hdr->e_err_max_bits);
@@ -634,6 +766,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         if (lane == 0 && p.scalars && sum_d != 0.0) atomicAdd(&p.scalars[VQ_S_SUM_MIN_D], sum_d);
     } else if (warp < 12) {
         // ============================================================ scan groups (thread == frame)
+        reg_inc<REGS_SCAN>();
         const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 4) >> 2;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
         const uint32_t key_mul = p.key_mul;
@@ -641,42 +774,51 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
+            uint32_t ch[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ch[j] = 0u;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
                 // The two scan groups take ALTERNATE code tiles (accumulator stage == group), so one group's TMEM loads and
                 // barrier waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
                 if ((qa & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = qa & 1u, sph = (qa >> 1) & 1u;
-                mbar_wait<20>(smem_u32(&ctl->acc_full[s]), sph);
+                mbar_spin(smem_u32(&ctl->acc_full[s]), sph);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4) VQ_TRACE_NT(12, it, nt);
+                uint32_t v[4][32];
+                {
+                    const uint32_t taddr = tmem + lane_base + s * TN;
+#if VQ_EXPERIMENT & 2                     /* timing experiment: no TMEM reads */
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[q][j] = taddr * (q + 1) + j;
+#else
+                    tc_ld32(taddr, v[0]);
+                    tc_ld32(taddr + 32, v[1]);
+                    tc_ld32(taddr + 64, v[2]);
+                    tc_ld32(taddr + 96, v[3]);
+                    tc_wait_ld();
+#endif
+                    tc_fence_before();
+                    mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                // all 128 columns are in registers: free the stage
+                    if (warp == 4) VQ_TRACE_NT(13, it, nt);
+                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int cbase = nt * TN + half * 64;
-                    uint32_t v0[32], v1[32];
-                    const uint32_t taddr = tmem + lane_base + s * TN + half * 64;
-#if VQ_EXPERIMENT & 2                     /* timing experiment: no TMEM reads */
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { v0[j] = taddr + j; v1[j] = taddr * 3 + j; }
-#else
-                    tc_ld32(taddr, v0);
-                    tc_ld32(taddr + 32, v1);
-                    tc_wait_ld();
-#endif
-                    if (half == 1) {
-                        tc_fence_before();
-                        mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));            // all 128 columns are in registers: free the stage
-                        if (warp == 4) VQ_TRACE_NT(13, it, nt);
-                    }
+                    const uint32_t (&v0)[32] = v[2 * half];
+                    const uint32_t (&v1)[32] = v[2 * half + 1];
                     uint32_t t1, t2;
 #if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
                     t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
 #else
-                    if (p.fold) scan64<2>(v0, v1, nullptr, key_mul, t1, t2);
-                    else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, key_mul, t1, t2);
-                    else scan64<0>(v0, v1, p.hn_off + cbase, key_mul, t1, t2);
+                    if (p.fold) scan64<2>(v0, v1, nullptr, key_mul, ch, t1, t2);
+                    else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, key_mul, ch, t1, t2);
+                    else scan64<0>(v0, v1, p.hn_off + cbase, key_mul, ch, t1, t2);
 #endif
-                    // fold the pair of this half tile into the running pair
+                    // fold this half tile into the running pair: r1 = best key, r2 = best key outside the winner's block
                     if (t1 > r1) {
                         r2 = max(r1, t2);
                         r1 = t1;
@@ -689,11 +831,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             }
             const uint32_t cb = it % p.cd, cph = (it / p.cd) & 1;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
+            r2 = max(r2, chains_runner_up(ch));                    // ... and outside the winner's residue chain: the exact runner-up
             Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1; c.pad = 0;
             cand[(cb * 2 + wg) * TM + r] = c;
             mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
             if (warp == 4) VQ_TRACE(9, it);
         }
+    } else {
+        reg_dec<REGS_ISSUER>();                                     // W_ALLOC: idle until the end
     }
 
     tc_fence_before();
@@ -768,8 +913,10 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
         p.fold = 1;
         p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES <= 227 * 1024 ? CD : 3;
     }
+    if (const char* e = getenv("VQ_K1_FOLD")) { if (atoi(e) == 0) { p.fold = 0; p.cd = CD; } }   // A/B switch for measurements
     p.a_const_col = 512 - 8;
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
+    if (const char* e = getenv("VQ_K1_PAIR")) p.pair = p.pair && atoi(e) != 0;   // A/B switch for measurements
     const int a_cols = (p.fold ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles

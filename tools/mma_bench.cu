@@ -47,6 +47,23 @@ __global__ void __launch_bounds__(384, 1) bench(int n_cols, int mode, int reps, 
         const bool leader = elect_one();
         const uint64_t bd = desc(smem_u32(smem)), ad = desc(smem_u32(smem + 32768));
         long long t0 = clock64();
+        if (mode == 4) {
+            // the kernel's pattern: a batch of 9 MMAs, commit, wait for completion, next batch
+            uint32_t ph = 0;
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    if (leader) mma_ts(tmem, tmem + 256 + uint32_t((k & 7) * 8), bd + uint64_t((k & 3) * 2) + uint64_t(((k >> 2) & 1) * 1024), idesc, k != 0);
+                if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                uint32_t ok = 0;
+                while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(ph) : "memory");
+                ph ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            long long t1 = clock64();
+            if (leader && blockIdx.x == 0) { out[0] = (t1 - t0) * 8 / 9; out[1] = 0; }
+            stop = 1;
+        } else {
         for (int r = 0; r < reps; ++r) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -63,8 +80,9 @@ __global__ void __launch_bounds__(384, 1) bench(int n_cols, int mode, int reps, 
         uint32_t ok = 0;
         while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
         long long t1 = clock64();
-        if (leader) { out[0] = t1 - t0; out[1] = t_issue - t0; }
+        if (leader && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t_issue - t0; }
         stop = 1;
+        }
     } else if (mode == 3 && warp < 8) {
         // accumulator readers: tcgen05.ld 32x32b.x32 in a loop
         uint32_t r[32];
@@ -81,7 +99,7 @@ __global__ void __launch_bounds__(384, 1) bench(int n_cols, int mode, int reps, 
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             sink += r[0] ^ r[31];
         }
-        if (sink == 0x12345) out[7] = sink;
+        if (sink == 0x12345 && blockIdx.x == 0) out[7] = sink;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -93,17 +111,18 @@ int main() {
     cudaMallocManaged(&out, 64);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     const int reps = 200;
-    const char* names[] = {"TS same D", "TS alternating D", "SS same D", "TS same D + 8 warps of tcgen05.ld"};
-    for (int mode = 0; mode < 4; ++mode)
+    const char* names[] = {"TS same D", "TS alternating D", "SS same D", "TS same D + 8 warps of tcgen05.ld", "TS batches of 9 + commit + wait"};
+    for (int grid : {148})
+    for (int mode = 0; mode < 5; ++mode)
         for (int n : {64, 128, 256}) {
             if (mode == 1 && n == 256) continue;     // two 256-column tiles + A would not fit
             for (int trial = 0; trial < 2; ++trial) {
                 out[0] = out[1] = 0;
-                bench<<<1, 384, 66 * 1024>>>(n, mode, reps, out);
+                bench<<<grid, 384, 66 * 1024>>>(n, mode, reps, out);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
             }
-            printf("%-36s N=%3d: %7.1f cycles/MMA to completion, %7.1f to issue  (ideal %d)\n", names[mode], n,
+            printf("grid %3d %-36s N=%3d: %7.1f cycles/MMA to completion, %7.1f to issue  (ideal %d)\n", grid, names[mode], n,
                    double(out[0]) / (reps * 8), double(out[1]) / (reps * 8), n / 2);
         }
     return 0;

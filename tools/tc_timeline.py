@@ -27,7 +27,7 @@ def main(n_utt=256, K=512, D=128):
     idx = torch.empty(n, t, dtype=torch.int64, device=dev)
     ws = torch.empty(int(lib.vq_workspace_bytes(n, t, K, d)), dtype=torch.uint8, device=dev)
     tiles = 32
-    trace = torch.zeros(15, tiles, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16, tiles, dtype=torch.int64, device=dev)
     for _ in range(3):
         rc = lib.vq_assign_debug(xd.data_ptr(), n, d, t, kd.data_ptr(), K, idx.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
                                  torch.cuda.current_stream().cuda_stream, trace.data_ptr(), tiles)
@@ -43,10 +43,10 @@ def main(n_utt=256, K=512, D=128):
         vals = [int(tr[e, i]) - t0 if int(tr[e, i]) else -1 for e in range(10)]
         rows.append(vals)
         print(f"{i:4d} " + " ".join(f"{v:12d}" for v in vals))
-    print("per code-tile probes, local tiles 8..15: mma_go(after acc_empty)  mma_commit  scan_go(after acc_full)  scan_released  scan_done")
+    print("per code-tile probes, local tiles 8..15: mma_go(after acc_empty)  mma_commit  scan_go(after acc_full)  scan_released  scan_done  mma_done_seen_by_issuer")
     fine = []
     for q in range(32):
-        vals = [int(tr[e, q]) - t0 if int(tr[e, q]) else -1 for e in range(10, 15)]
+        vals = [int(tr[e, q]) - t0 if int(tr[e, q]) else -1 for e in range(10, 16)]
         fine.append(vals)
         print(f"tile {8 + q // 4} nt {q % 4}: " + " ".join(f"{v:10d}" for v in vals))
     os.makedirs("gpurun_out", exist_ok=True)
