@@ -103,7 +103,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // SLEEP_NS > 0 backs off with nanosleep between probes (used where a few hundred ns of wake-up latency is harmless).
-constexpr int REGS_ISSUER = 40, REGS_FRONT = 104, REGS_SCAN = 184;    // 4*40 + 4*104 + 8*184 = 2048 = 16 warps x 128
+constexpr int REGS_ISSUER = 40, REGS_FRONT = 120, REGS_SCAN = 176;    // 4*40 + 4*120 + 8*176 = 2048 = 16 warps x 128
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -126,6 +126,18 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
         if (++spins > (SPIN_LIMIT << 6)) __trap();
     } while (!ok);
 }
+// Position in a ring of n slots plus the mbarrier phase of that lap.  Kept incrementally: `q % n` / `q / n` with a run-time
+// n is a ~40-instruction emulated division, and on the single-issuer warps that sat on the critical path of every tile.
+struct Ring {
+    uint32_t i = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t n) { if (++i == n) { i = 0; ph ^= 1u; } }
+};
+// (utterance, first frame) of the tiles a CTA visits: tile += step without dividing by tiles_per_utt every time
+struct TileWalk {
+    int n, t;     // utterance, tile index inside the utterance
+    __device__ __forceinline__ TileWalk(int tile, int per) : n(tile / per), t(tile % per) {}
+    __device__ __forceinline__ void advance(int step, int per) { t += step; while (t >= per) { t -= per; ++n; } }
+};
 // One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
 // asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
 // compiler wrap every tcgen05.mma / TMA in an ELECT + R2UR.BROADCAST loop, ~190 cycles per instruction).
@@ -413,13 +425,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         // ============================================================ x producer
         reg_dec<REGS_ISSUER>();
         const bool leader = elect_one();
-        uint32_t q = 0;
-        for (int tile = first; tile < p.n_tiles; tile += step) {
-            const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TM;
+        uint32_t q = 0, it = 0;
+        TileWalk tw(first, p.tiles_per_utt);
+        for (int tile = first; tile < p.n_tiles; tile += step, ++it, tw.advance(step, p.tiles_per_utt)) {
+            const int n = tw.n, t0 = tw.t * TM;
             for (int ch = 0; ch < p.n_xch; ++ch, ++q) {
                 const uint32_t s = q % XS, ph = (q / XS) & 1;
                 mbar_wait<500>(smem_u32(&ctl->x_empty[s]), ph ^ 1);
-                if (ch == 0) VQ_TRACE(0, q / p.n_xch);
+                if (ch == 0) VQ_TRACE(0, it);
                 if (leader) {
 #if VQ_EXPERIMENT & 32                    /* timing experiment: no x loads */
                     mbar_arrive(smem_u32(&ctl->x_full[s]));
@@ -446,11 +459,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         } else if (p.pair) {
             // streaming, N = 256 operands: a ring of PAIR stages (two adjacent 16 KB tiles: code tiles nt and nt+1 of one depth block)
             const uint32_t n_ps = uint32_t(p.b_stages) >> 1;
-            uint32_t q = 0;
+            Ring rb;
             for (int tile = first; tile < p.n_tiles; tile += step)
                 for (int nt = 0; nt < p.n_nt; nt += 2)
-                    for (int kb = 0; kb < p.n_kb; ++kb, ++q) {
-                        const uint32_t s = q % n_ps, ph = (q / n_ps) & 1;
+                    for (int kb = 0; kb < p.n_kb; ++kb, rb.next(n_ps)) {
+                        const uint32_t s = rb.i, ph = rb.ph;
                         mbar_wait<100>(smem_u32(&ctl->b_empty[s]), ph ^ 1);
                         if (leader) {
                             mbar_expect_tx(smem_u32(&ctl->b_full[s]), 2 * B_STAGE_BYTES);
@@ -459,11 +472,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                     }
         } else {
-            uint32_t q = 0;
+            Ring rb;
             for (int tile = first; tile < p.n_tiles; tile += step)
                 for (int nt = 0; nt < p.n_nt; ++nt)
-                    for (int kb = 0; kb < p.n_kb; ++kb, ++q) {
-                        const uint32_t s = q % p.b_stages, ph = (q / p.b_stages) & 1;
+                    for (int kb = 0; kb < p.n_kb; ++kb, rb.next(uint32_t(p.b_stages))) {
+                        const uint32_t s = rb.i, ph = rb.ph;
                         mbar_wait<100>(smem_u32(&ctl->b_empty[s]), ph ^ 1);
                         if (leader) {
                             mbar_expect_tx(smem_u32(&ctl->b_full[s]), B_STAGE_BYTES);
@@ -476,24 +489,27 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         reg_dec<REGS_ISSUER>();
         {
             const bool leader = elect_one();
-            uint32_t qa = 0, qb = 0, it = 0;
-            for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
-                const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
-                mbar_wait<64>(smem_u32(&ctl->a_full[a]), aph);
+            uint32_t qa = 0, it = 0;
+            Ring ra, rb;                                      // A buffers; streaming B stages
+            // loop-invariant operands of the resident fast path
+            const uint64_t bd0 = b_desc_base(smem_u32(bs_base));
+            const uint64_t kb_stride = uint64_t(p.n_nt) * uint64_t(B_STAGE_BYTES >> 4);
+            const uint64_t hd0 = hn_desc(smem_u32(hn_b));
+            const uint32_t a_const = tmem + uint32_t(p.a_const_col);
+            const int n_kb = p.n_kb, n_nt = p.n_nt;
+            const bool fold = p.fold != 0, resident = p.resident != 0, pair = p.pair != 0;
+            const uint32_t a_bufs = uint32_t(p.a_bufs);
+            for (int tile = first; tile < p.n_tiles; tile += step, ++it, ra.next(a_bufs)) {
+                const uint32_t a = ra.i, aph = ra.ph;
+                mbar_spin(smem_u32(&ctl->a_full[a]), aph);
                 tc_fence_after();
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
 #if !(VQ_EXPERIMENT & (16 | 64 | 128))
-                if (p.resident && it != 0) {
+                if (resident && it != 0) {
                     // Steady state with the codebook resident in shared memory (every B tile is known to have landed after
                     // the first frame tile): nothing but barrier waits between straight-line MMA batches.
-                    const uint64_t bd0 = b_desc_base(smem_u32(bs_base));
-                    const uint64_t kb_stride = uint64_t(p.n_nt) * uint64_t(B_STAGE_BYTES >> 4);
-                    const uint64_t hd0 = hn_desc(smem_u32(hn_b));
-                    const uint32_t a_const = tmem + uint32_t(p.a_const_col);
-                    const int n_kb = p.n_kb, n_nt = p.n_nt;
-                    const bool fold = p.fold != 0;
-                    if (p.pair) {
+                    if (pair) {
                         for (int nt = 0; nt < n_nt; nt += 2, qa += 2) {
                             const uint32_t sph = (qa >> 1) & 1u;
                             mbar_spin(smem_u32(&ctl->acc_empty[0]), sph ^ 1);
@@ -508,14 +524,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                             __syncwarp();
                             VQ_TRACE_NT(11, it, nt);
-                            if (p.trace && p.trace_tiles >= 32) {       // probe only: when does the ISSUER see the batch complete?
+                            if (p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
                                 mbar_spin(smem_u32(&ctl->acc_full[0]), sph);
                                 VQ_TRACE_NT(15, it, nt);
                             }
                         }
                     } else {
                         for (int nt = 0; nt < n_nt; ++nt, ++qa) {
-                            const uint32_t st = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
+                            const uint32_t st = qa & 1u, sph = (qa >> 1) & 1u;      // two accumulator stages
                             mbar_spin(smem_u32(&ctl->acc_empty[st]), sph ^ 1);
                             tc_fence_after();
                             VQ_TRACE_NT(10, it, nt);
@@ -526,7 +542,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                             __syncwarp();
                             VQ_TRACE_NT(11, it, nt);
-                            if (p.trace && p.trace_tiles >= 32) {       // probe only: when does the ISSUER see the batch complete?
+                            if (p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
                                 mbar_spin(smem_u32(&ctl->acc_full[st]), sph);
                                 VQ_TRACE_NT(15, it, nt);
                             }
@@ -558,9 +574,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                     tc_fence_after();
                                 }
                             } else {
-                                const uint32_t n_ps = uint32_t(p.b_stages) >> 1;
-                                ps = qb % n_ps;
-                                mbar_wait<0>(smem_u32(&ctl->b_full[ps]), (qb / n_ps) & 1);
+                                ps = rb.i;
+                                mbar_wait<0>(smem_u32(&ctl->b_full[ps]), rb.ph);
                                 tc_fence_after();
                                 bs = 2 * ps;
                             }
@@ -570,7 +585,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                 if (leader)
                                     tc_mma_ts(tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), bd + uint64_t(k4 * 2), IDESC256,
                                               (kb | k4) != 0 ? 1u : 0u);
-                            if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[ps])); ++qb; }
+                            if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[ps])); rb.next(uint32_t(p.b_stages) >> 1); }
                         }
                         if (p.fold && leader)
                             tc_mma_ts(tmem, tmem + uint32_t(p.a_const_col), hn_desc(smem_u32(hn_b + size_t(nt) * HN_TILE_BYTES)), IDESC256, 1u);
@@ -579,7 +594,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                 } else
                 for (int nt = 0; nt < p.n_nt; ++nt, ++qa) {
-                    const uint32_t s = qa % p.acc_stages, sph = (qa / p.acc_stages) & 1;
+                    const uint32_t s = qa & 1u, sph = (qa >> 1) & 1u;
                     mbar_wait<32>(smem_u32(&ctl->acc_empty[s]), sph ^ 1);
                     tc_fence_after();
                     VQ_TRACE_NT(10, it, nt);
@@ -590,8 +605,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             bs = kb * p.n_nt + nt;
                             if (it == 0) mbar_wait<0>(smem_u32(&ctl->b_full[bs]), 0);
                         } else {
-                            bs = qb % p.b_stages;
-                            mbar_wait<0>(smem_u32(&ctl->b_full[bs]), (qb / p.b_stages) & 1);
+                            bs = rb.i;
+                            mbar_wait<0>(smem_u32(&ctl->b_full[bs]), rb.ph);
                         }
                         tc_fence_after();
                         const uint64_t bd = b_desc_base(smem_u32(bs_base + size_t(bs) * B_STAGE_BYTES));
@@ -611,7 +626,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #endif
                             }
                         }
-                        if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[bs])); ++qb; }
+                        if (!p.resident) { if (leader) tc_commit(smem_u32(&ctl->b_empty[bs])); rb.next(uint32_t(p.b_stages)); }
                     }
                     if (p.fold && leader)   // one more k-step: [1,1,1,0..] x (B - ||e||^2/2 as hi+mid+lo) adds the offset in the tensor core
                         tc_mma_ts(d_tmem, tmem + uint32_t(p.a_const_col), hn_desc(smem_u32(hn_b + size_t(nt) * HN_TILE_BYTES)), IDESC, 1u);
@@ -636,16 +651,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         }
 
         // back stage of local tile j: merge the two scan groups, decide, write
+        Ring rfin;                                            // hand-off slot of the next tile to finish (calls are in order of j)
+        TileWalk wfin(first, p.tiles_per_utt);
         auto finish = [&](uint32_t j) {
-            const int tile = first + int(j) * step;
-            const uint32_t cb = j % p.cd, cph = (j / p.cd) & 1;
+            const uint32_t cb = rfin.i, cph = rfin.ph;
+            rfin.next(uint32_t(p.cd));
             if (wq == 0) VQ_TRACE(6, j);
             mbar_wait<500>(smem_u32(&ctl->cand_full[cb]), cph);
             if (wq == 0) VQ_TRACE(7, j);
             const Cand ca = cand[(cb * 2 + 0) * TM + r], cc = cand[(cb * 2 + 1) * TM + r];
             const float2 st = rowstat[cb * TM + r];
             mbar_arrive_warp(smem_u32(&ctl->cand_empty[cb]));
-            const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TM + r;
+            const int n = wfin.n, t = wfin.t * TM + r;
+            wfin.advance(step, p.tiles_per_utt);
             const bool in_tile = t < p.T;
             bool unsafe = false;
             const int64_t row = int64_t(n) * p.T + t;
@@ -722,8 +740,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             }
         };
 
-        for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
-            const uint32_t a = it % p.a_bufs, aph = (it / p.a_bufs) & 1;
+        Ring ra, rstat;                                       // A buffer being filled; row-statistics slot of this tile
+        for (int tile = first; tile < p.n_tiles; tile += step, ++it, ra.next(uint32_t(p.a_bufs)), rstat.next(uint32_t(p.cd))) {
+            const uint32_t a = ra.i, aph = ra.ph;
             mbar_wait<500>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
             tc_fence_after();
             if (wq == 0) VQ_TRACE(3, it);
@@ -754,7 +773,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 mbar_arrive_warp(smem_u32(&ctl->x_empty[s]));                      // the stage's data now lives in registers
                 tc_st16(a_tmem + uint32_t(ch * (XCH / 2)), pk);
             }
-            rowstat[(it % p.cd) * TM + r] = make_float2(xx, rr);                   // read back by this same thread in finish()
+            rowstat[rstat.i * TM + r] = make_float2(xx, rr);                   // read back by this same thread in finish()
             tc_wait_st();
             tc_fence_before();
             mbar_arrive_warp(smem_u32(&ctl->a_full[a]));
@@ -771,7 +790,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
         const uint32_t key_mul = p.key_mul;
         uint32_t qa = 0, it = 0;
-        for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
+        Ring rc;                                              // hand-off slot of this tile
+        for (int tile = first; tile < p.n_tiles; tile += step, ++it, rc.next(uint32_t(p.cd))) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
             uint32_t ch[16];
@@ -829,7 +849,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 if (warp == 4) VQ_TRACE_NT(14, it, nt);
             }
-            const uint32_t cb = it % p.cd, cph = (it / p.cd) & 1;
+            const uint32_t cb = rc.i, cph = rc.ph;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
             r2 = max(r2, chains_runner_up(ch));                    // ... and outside the winner's residue chain: the exact runner-up
             Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1; c.pad = 0;

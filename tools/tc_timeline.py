@@ -26,7 +26,7 @@ def main(n_utt=256, K=512, D=128):
     xd, kd = x.to(dev), code.to(dev)
     idx = torch.empty(n, t, dtype=torch.int64, device=dev)
     ws = torch.empty(int(lib.vq_workspace_bytes(n, t, K, d)), dtype=torch.uint8, device=dev)
-    tiles = 32
+    tiles = 64 if os.environ.get("TL_PROBE") else 32      # 64 enables the issuer-side completion probe (it serialises N=128 batches)
     trace = torch.zeros(16, tiles, dtype=torch.int64, device=dev)
     for _ in range(3):
         rc = lib.vq_assign_debug(xd.data_ptr(), n, d, t, kd.data_ptr(), K, idx.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
