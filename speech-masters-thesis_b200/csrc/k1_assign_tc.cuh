@@ -802,7 +802,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 // barrier waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
                 if ((qa & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = qa & 1u, sph = (qa >> 1) & 1u;
-                mbar_spin(smem_u32(&ctl->acc_full[s]), sph);
+                // suspended wait: as fast as a spinning test_wait (measured) without burning a third of the issue slots
+                mbar_wait<0>(smem_u32(&ctl->acc_full[s]), sph);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4) VQ_TRACE_NT(12, it, nt);
