@@ -183,6 +183,223 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
     }
 }
 
+// ---- asynchronous variant (T % 4 == 0, 16-byte aligned tensors): one persistent CTA per SM; the x (and grad) tile AND the
+// gathered codebook rows of the next one or two work units are in flight (cp.async) while the current unit is computed
+// entirely from shared memory.  The synchronous kernel above keeps only ~half a tile per CTA in flight between its
+// barriers and measured 0.47 of the HBM peak; this one is bound by the copy engine instead of by load latency.
+//   work unit = 64 frames x (up to) 128 depths;  stage = [x tile 32 KB] (+ [grad tile 32 KB]) + [codebook rows 34 KB]
+// Gather mapping: a warp copies 4 codebook rows x 8 depths per instruction (lane = 4*depth + row), which makes the
+// transposing 4-byte writes into Es[depth][frame] (row stride 68 floats) hit 32 different banks.
+constexpr int GA_THREADS = 512;
+constexpr int GA_DS = 128;                   // depths per work unit
+constexpr int GA_ES = G_TT + 4;              // Es row stride (floats)
+constexpr int GA_RING = 8, GA_AHEAD = 4;     // index/mask ring: slots, prefetch distance in work units
+template <int MODE> struct GaCfg {
+    static constexpr int NST = MODE == GM_BWD ? 2 : 3;                              // stages in the ring
+    static constexpr int NX = MODE == GM_DECODE ? 0 : (MODE == GM_BWD ? 2 : 1);     // streamed input tiles per stage
+    static constexpr int STAGE_FLOATS = NX * GA_DS * G_TT + GA_DS * GA_ES;
+    static constexpr size_t SMEM = size_t(NST) * STAGE_FLOATS * 4 + GA_RING * G_TT * 12;
+    static constexpr int CTAS_PER_SM = MODE == GM_DECODE ? 2 : 1;    // decode has no streamed input: 2 x 110 KB fit, and a second CTA
+                                                                      // covers the L2 latency of the gather
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(GA_THREADS, GaCfg<MODE>::CTAS_PER_SM)
+gather_async_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
+                    const float* __restrict__ k, const float* __restrict__ grad_xq, const float* __restrict__ grad_commit,
+                    int N, int D, int T, int K, float* __restrict__ out, double* __restrict__ scalars,
+                    float* __restrict__ results, unsigned int total_blocks) {
+    constexpr int NST = GaCfg<MODE>::NST, NX = GaCfg<MODE>::NX, STAGE_FLOATS = GaCfg<MODE>::STAGE_FLOATS;
+    extern __shared__ __align__(16) float smem[];
+    int64_t* s_idx = reinterpret_cast<int64_t*>(smem + size_t(NST) * STAGE_FLOATS);   // [GA_RING][G_TT]  ring over work units
+    float* s_mask = reinterpret_cast<float*>(s_idx + GA_RING * G_TT);                  // [GA_RING][G_TT]
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    __shared__ int4 s_loc[GA_RING];           // (utterance, first frame, first depth, exists) of the units in the ring
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_per_utt = (T + G_TT - 1) / G_TT;
+    const int n_slices = (D + GA_DS - 1) / GA_DS;
+    const int n_units = N * tiles_per_utt * n_slices;                              // host guarantees < 2^31
+    const int u0 = blockIdx.x, step = gridDim.x;
+    const bool have_grad = MODE == GM_BWD && grad_xq != nullptr;
+
+    auto locate = [&](int u, int& n, int& t0, int& d0) {
+        const int tile = u / n_slices;
+        d0 = (u - tile * n_slices) * GA_DS;
+        n = tile / tiles_per_utt;
+        t0 = (tile - n * tiles_per_utt) * G_TT;
+    };
+    // indices and mask of local unit j (= global unit u) -> ring slot j % GA_RING, asynchronously, GA_AHEAD units ahead of
+    // their first use (they come from HBM: a synchronous load would put a DRAM round trip into every iteration).
+    // The two integer divisions of locate() run here once per unit, on 64 threads; everyone else reads s_loc.
+    auto prefetch_im = [&](int j, int u) {
+        if (tid < G_TT) {
+            const int slot = j & (GA_RING - 1);
+            int4 loc = make_int4(0, 0, 0, 0);
+            bool copied = false;
+            if (u < n_units) {
+                int n, t0, d0;
+                locate(u, n, t0, d0);
+                loc = make_int4(n, t0, d0, 1);
+                const int t = t0 + tid;
+                if (t < T) {
+                    cp_async8(s_idx + slot * G_TT + tid, idx + int64_t(n) * T + t);
+                    if (mask) cp_async4(s_mask + slot * G_TT + tid, mask + int64_t(n) * T + t);
+                    else s_mask[slot * G_TT + tid] = 1.f;
+                    copied = true;
+                }
+            }
+            if (!copied) { s_idx[slot * G_TT + tid] = 0; s_mask[slot * G_TT + tid] = 0.f; }
+            if (tid == 0) s_loc[slot] = loc;
+        }
+    };
+    auto issue = [&](int st, int ring) {
+        const int4 loc = s_loc[ring];
+        if (loc.w) {
+            const int n = loc.x, t0 = loc.y, d0 = loc.z;
+            const int dn = min(GA_DS, D - d0);
+            float* S = smem + size_t(st) * STAGE_FLOATS;
+            if (NX > 0) {
+                // streamed tiles: 128 depths x 16 chunks of 4 frames, 4 chunks per thread
+#pragma unroll
+                for (int r = 0; r < GA_DS * (G_TT / 4) / GA_THREADS; ++r) {
+                    const int i = tid + r * GA_THREADS, d = i >> 4, c4 = (i & 15) * 4;
+                    if (d < dn && t0 + c4 < T) {
+                        const int64_t o = (int64_t(n) * D + d0 + d) * T + t0 + c4;
+                        cp_async16(S + d * G_TT + c4, x + o);
+                        if (NX > 1 && have_grad) cp_async16(S + GA_DS * G_TT + d * G_TT + c4, grad_xq + o);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // codebook rows of unit u through registers (4-byte cp.async is serialised per element by the hardware: measured
+    // 1.6x slower than the synchronous kernel): warp w takes frames 4w .. 4w+3 and all depth blocks of 8; the loads are
+    // issued one iteration before the stores, so their L2 latency hides behind the computation of the current unit.
+    const int g_r = 4 * warp + (lane & 3), g_dd = lane >> 2;
+    auto gather_ld = [&](int ring, float (&ev)[GA_DS / 8]) {
+        const int4 loc = s_loc[ring];
+        if (loc.w) {
+            const int d0 = loc.z;
+            const int dn = min(GA_DS, D - d0);
+            const int code = int(min(max(s_idx[ring * G_TT + g_r], int64_t(0)), int64_t(K - 1)));
+            const float* src = k + size_t(code) * D + d0 + g_dd;
+#pragma unroll
+            for (int db = 0; db < GA_DS / 8; ++db) ev[db] = (8 * db + g_dd < dn) ? __ldg(src + 8 * db) : 0.f;
+        }
+    };
+    auto gather_st = [&](int st, const float (&ev)[GA_DS / 8]) {
+        float* dst = smem + size_t(st) * STAGE_FLOATS + NX * GA_DS * G_TT + g_dd * GA_ES + g_r;
+#pragma unroll
+        for (int db = 0; db < GA_DS / 8; ++db) dst[8 * db * GA_ES] = ev[db];
+    };
+
+    float gscale = 0.f;
+    if (MODE == GM_BWD) gscale = float(2.0 * double(*grad_commit) / (scalars[VQ_S_MASK_SUM] * double(D)));
+    double sq = 0.0, sq_all = 0.0, msum_local = 0.0;
+
+#pragma unroll
+    for (int j = 0; j < GA_AHEAD; ++j) prefetch_im(j, u0 + j * step);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float ev[GA_DS / 8];
+#pragma unroll
+    for (int j = 0; j < GA_DS / 8; ++j) ev[j] = 0.f;
+    gather_ld(0, ev);
+    gather_st(0, ev);
+#pragma unroll
+    for (int j = 0; j < NST - 1; ++j) issue(j, j);                // (each call commits one group)
+
+    int it = 0;
+    for (int u = u0; u < n_units; u += step, ++it) {
+        gather_ld((it + 1) & (GA_RING - 1), ev);                  // stored at the end of this iteration
+        prefetch_im(it + GA_AHEAD, u + GA_AHEAD * step);          // joins the copy group committed by issue() below
+        cp_async_wait<NST - 2>();                                 // this thread's copies of unit u have landed
+        __syncthreads();                                          // ... everyone's; the stage of unit u-1 is free again
+        issue((it + NST - 1) % NST, (it + NST - 1) & (GA_RING - 1));
+
+        const int4 cur = s_loc[it & (GA_RING - 1)];
+        const int n = cur.x, t0 = cur.y, d0 = cur.z;
+        const int tt = min(G_TT, T - t0), dn = min(GA_DS, D - d0);
+        const float* S = smem + size_t(it % NST) * STAGE_FLOATS;
+        const float* Es = S + NX * GA_DS * G_TT;
+        const float* sm = s_mask + (it & (GA_RING - 1)) * G_TT;
+        const int t4 = (tid & 15) * 4, dg = tid >> 4;
+        if (MODE == GM_FWD && d0 == 0 && tid < G_TT) msum_local += double(sm[tid]);
+        if (t4 < tt) {
+            const float4 m4 = *reinterpret_cast<const float4*>(sm + t4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            const float vv[4] = {m4.x != 0.f ? 1.f : 0.f, m4.y != 0.f ? 1.f : 0.f, m4.z != 0.f ? 1.f : 0.f, m4.w != 0.f ? 1.f : 0.f};
+            float accf[4] = {0.f, 0.f, 0.f, 0.f};                 // sum over depth of (x_d - x)^2, per frame
+            float* dst = out + (int64_t(n) * D + d0) * T + t0 + t4;
+#pragma unroll 4
+            for (int d = dg; d < dn; d += GA_THREADS / 16) {
+                const float4 e4 = *reinterpret_cast<const float4*>(Es + d * GA_ES + t4);
+                const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+                float oo[4];
+                if (MODE == GM_DECODE) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oo[j] = ee[j];
+                } else {
+                    const float4 x4 = *reinterpret_cast<const float4*>(S + d * G_TT + t4);
+                    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+                    if (MODE == GM_FWD) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float diff = __fsub_rn(ee[j], xx[j]);                   // (x_d - x)
+                            oo[j] = __fmul_rn(__fadd_rn(xx[j], diff), mm[j]);             // (x + (x_d - x)) * mask
+                            accf[j] = fmaf(diff, diff, accf[j]);
+                        }
+                    } else {
+                        float gg[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (have_grad) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(S + GA_DS * G_TT + d * G_TT + t4);
+                            gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float g = __fmul_rn(gg[j], mm[j]);
+                            if (vv[j] != 0.f) g = fmaf(gscale, __fsub_rn(xx[j], ee[j]), g);
+                            oo[j] = g;
+                        }
+                    }
+                }
+                st_stream4(reinterpret_cast<float4*>(dst + int64_t(d) * T), make_float4(oo[0], oo[1], oo[2], oo[3]));
+            }
+            if (MODE == GM_FWD) {
+                sq_all += double((accf[0] + accf[1]) + (accf[2] + accf[3]));     // every frame: the numerator of `fit`
+                sq += double((accf[0] * vv[0] + accf[1] * vv[1]) + (accf[2] * vv[2] + accf[3] * vv[3]));   // valid frames: commit loss
+            }
+        }
+        gather_st((it + 1) % NST, ev);                            // that stage's rows were last read NST-1 iterations ago
+    }
+    cp_async_wait<0>();
+    if (MODE == GM_FWD) {
+        double s1 = block_sum(sq, red);
+        double s2 = block_sum(msum_local, red);
+        double s3 = block_sum(sq_all, red);
+        if (tid == 0) {
+            atomicAdd(&scalars[VQ_S_SUM_MIN_D], s3);
+            atomicAdd(&scalars[VQ_S_COMMIT_SQ], s1);
+            atomicAdd(&scalars[VQ_S_MASK_SUM], s2);
+            __threadfence();
+            unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(&scalars[VQ_S_TICKET]), 1u);
+            is_last = (ticket == total_blocks - 1);
+        }
+        __syncthreads();
+        if (is_last && tid == 0) {
+            __threadfence();
+            volatile double* sc = scalars;
+            results[VQ_R_COMMIT] = float(sc[VQ_S_COMMIT_SQ] / (sc[VQ_S_MASK_SUM] * double(D)));
+            results[VQ_R_FIT] = float(sc[VQ_S_SUM_MIN_D] / double(K));
+            *reinterpret_cast<unsigned int*>(&scalars[VQ_S_TICKET]) = 0u;
+        }
+    }
+}
+
 // out[j, :] = x[n_j, :, t_j]   (restart rows; bottleneck.py:40,70 touches only K rows this way)
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t n_rows,
                                    int64_t N, int D, int64_t T, float* __restrict__ out) {

@@ -12,19 +12,6 @@ constexpr int E_TT = 128;        // frames per tile      (fallback kernel for em
 constexpr int E_DS = 32;         // depth slice staged at a time
 constexpr int E_THREADS = 256;
 
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // ---- sorted-run kernels.  Tiles of 64 frames x (up to 64 or 128) depths stream through a cp.async ring; one warp
 // bitonic-sorts the NEXT tile's (code, frame) keys while the other 15 walk the current tile's rows in code order.  A run of
 // equal codes is summed in registers (lane == depth) by the warp in whose row range it STARTS, so no two warps ever touch

@@ -49,6 +49,23 @@ static int launch_gather_v(const float* x, const int64_t* idx, const float* mask
 }
 
 template <int MODE>
+static int launch_gather_async(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,
+                               const float* grad_commit, int64_t N, int D, int64_t T, int K, float* out, double* scalars,
+                               float* results, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        VQ_CUDA_OK(cudaFuncSetAttribute(gather_async_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GaCfg<MODE>::SMEM)));
+        configured = true;
+    }
+    const int64_t units = N * ((T + G_TT - 1) / G_TT) * ((D + GA_DS - 1) / GA_DS);
+    const int grid = int(std::min<int64_t>(units, int64_t(num_sms()) * GaCfg<MODE>::CTAS_PER_SM));
+    gather_async_kernel<MODE><<<grid, GA_THREADS, GaCfg<MODE>::SMEM, stream>>>(x, idx, mask, k, grad_xq, grad_commit, int(N), D, int(T), K,
+                                                                               out, scalars, results, (unsigned int)grid);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODE>
 static int launch_gather(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,
                          const float* grad_commit, int64_t N, int D, int64_t T, int K, float* out, double* scalars,
                          float* results, cudaStream_t stream) {
@@ -58,6 +75,13 @@ static int launch_gather(const float* x, const int64_t* idx, const float* mask, 
     bool vec = MODE == GM_BWD && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) && aligned(mask);
     static const char* force = getenv("VQ_K2_VEC");          // A/B switch for experiments: 0 = 4-byte path, 1 = 16-byte path
     if (force && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) && aligned(mask)) vec = force[0] == '1';
+    // default: the asynchronous persistent kernel whenever 16-byte copies are legal
+    static const char* sync_only = getenv("VQ_K2_SYNC");       // A/B switch: 1 = the synchronous kernels below
+    const int64_t units = N * ((T + G_TT - 1) / G_TT) * ((D + GA_DS - 1) / GA_DS);
+    // (decode is a pure 227 MB write: the synchronous kernel with its L1-resident codebook measured 0.060 ms against 0.066)
+    if (MODE != GM_DECODE && !(sync_only && sync_only[0] == '1') && (T % 4 == 0) && aligned(x) && aligned(out) && aligned(grad_xq) &&
+        (mask == nullptr || true) && units < (int64_t(1) << 31) && T < (int64_t(1) << 31))
+        return launch_gather_async<MODE>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
     if (vec) return launch_gather_v<MODE, true>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
     return launch_gather_v<MODE, false>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
 }
