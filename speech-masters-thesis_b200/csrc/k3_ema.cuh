@@ -240,6 +240,11 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
     }
 }
 
+// (Tried and measured on B200, K=512, D=128, 256 utterances -- not kept: an "owner computes" variant without the sort
+//  [TMA boxes + mbarrier ring, warp w owns code % 30 == w, one prep warp publishing per-owner frame masks]: 0.122 ms
+//  against 0.115 ms for the kernel above.  With idle consumers the same ring streams the valid tiles in 0.068 ms, i.e.
+//  2.8 TB/s: 64-frame tiles of a 64-deep slice are 256-byte pieces at a stride of T*4 bytes, which is what bounds both.)
+
 // Large-K variant: rows of one tile rarely share a code, so privatisation buys nothing; transpose the
 // tile through shared memory and issue depth-coalesced FP32 reductions straight to L2.
 __global__ void __launch_bounds__(E_THREADS)
