@@ -31,6 +31,8 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
     __shared__ long long row_off[S_BM];      // offset of x[n, 0, t] for each tile row, -1 when out of range
     __shared__ double red[32];
 
+    // (LIST runs as a programmatic dependent of the tcgen05 kernel: nothing that kernel wrote may be read before this)
+    if (LIST) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t tiles_per_utt = (T + S_BM - 1) / S_BM;

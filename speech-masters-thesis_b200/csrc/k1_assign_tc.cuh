@@ -436,6 +436,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     const uint32_t a_col0 = uint32_t(p.acc_stages) * TN, a_stride = uint32_t(p.Dp) >> 1;   // A buffers follow the accumulator stages
 
     const int first = blockIdx.x, step = gridDim.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // the exact re-scan kernel may be set up from now on
 
     // Register file re-split (the CTA owns all 64 K registers at 128 per thread): the four issuer warps and the front
     // group give registers to the scan groups, which then hold a whole 128-column accumulator stage in registers and

@@ -189,9 +189,20 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         // list tiles x code slices, so that a handful of rows still spreads over the machine
         const int splits = std::max(1, std::min(16, (K + S_BN - 1) / S_BN));
         const int gx = int(std::min<int64_t>(std::max(1, 4 * num_sms() / splits), (N * T + S_BM - 1) / S_BM));
-        assign_simt_kernel<true><<<dim3(gx, splits), 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
-                                                                     w.unsafe_rows, w.hdr, w.list_keys);
-        VQ_CUDA_OK(cudaGetLastError());
+        // Programmatic dependent launch: the kernel is set up while the main kernel still runs (which signals
+        // launch_dependents right after its prologue) and waits on griddepcontrol.wait before it reads the count, so the
+        // usual empty-worklist case costs ~3 us less than a serialised launch.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, splits);
+        cfg.blockDim = dim3(256);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (g_prof.on && pslot >= 0) ? 0 : 1;          // (event records between the two kernels serialise them anyway)
+        VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_simt_kernel<true>, x, N, int(D), T, k, (const float*)w.ee, K, idx, min_d, scalars,
+                                      (const int*)w.unsafe_rows, w.hdr, w.list_keys));
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));

@@ -180,6 +180,7 @@ SHAPES = [  # (N, D, T, K, clustered)
     (5, 16, 1, 8, False),         # T == 1
     (2, 512, 96, 640, False),
     (1, 8, 2000, 3, True),
+    (2, 192, 64, 300, True),      # two depth slices in the asynchronous K2 kernel, the second one partial
 ]
 
 
@@ -441,3 +442,24 @@ def test_device_side_restart_rows(vq):
     tiny_x, tiny_m = x[:, :, :8].contiguous(), mask[:, :, :8].contiguous()
     fresh(tiny_x.to(DEV), tiny_m.to(DEV))
     assert fresh.init and fresh.k.shape == (K, D) and bool(torch.isfinite(fresh.k).all())
+
+
+def test_three_accumulator_stage_mode(vq, monkeypatch):
+    """VQ_K1_STAGES=3 (three N = 128 accumulator stages, constant operand of the folded k-step read from shared memory
+    through a stride-0 descriptor) must give the same indices as the default two-stage mode and as the oracle."""
+    gen = torch.Generator().manual_seed(5)
+    K, D = 512, 128
+    code = torch.randn(K, D, generator=gen)
+    lengths = torch.tensor([512, 300, 256, 131])
+    x, mask = O.synthetic_batch(lengths, D, gen, codebook=code)
+    x = x[:, :, :512].contiguous()
+    mask = mask[:, :, :512].contiguous()
+    rows, _, _ = O.flatten_nct(x, mask)
+    o_l = O.assign(rows, code)[0]
+    xd, kd = x.to(DEV), code.to(DEV)
+    base = vq.assign(xd, kd, algo="tc")[0].cpu()
+    monkeypatch.setenv("VQ_K1_STAGES", "3")
+    three = vq.assign(xd, kd, algo="tc")[0].cpu()
+    monkeypatch.delenv("VQ_K1_STAGES")
+    assert torch.equal(base, three)
+    check_indices(rows, code, o_l, three)
