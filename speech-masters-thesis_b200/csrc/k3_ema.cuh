@@ -31,6 +31,7 @@ constexpr int ER_PER = (ER_TT + ER_WARPS - 2) / (ER_WARPS - 1);   // sorted rows
 // then never loaded.  One warp per tile.
 __global__ void __launch_bounds__(256) ema_tile_flags_kernel(const float* __restrict__ mask, int64_t N, int64_t T, int tiles_per_utt,
                                                             unsigned char* __restrict__ flags) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // the accumulate kernel may start zeroing its slab
     const int64_t tile = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= N * tiles_per_utt) return;
@@ -93,6 +94,8 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
     int ld_j = int(first % tiles_per_utt);
     const int step_j = int(step % tiles_per_utt);
     const int64_t step_n = step / tiles_per_utt;
+    // launched as a programmatic dependent of ema_tile_flags_kernel: everything above overlapped it, the flags are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned char ld_flag = (tile_flags && first < n_tiles) ? tile_flags[first] : 1;
 
     auto issue = [&](int st) {

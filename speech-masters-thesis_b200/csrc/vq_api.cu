@@ -285,7 +285,18 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
         }
         const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
         const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, num_sms() / slices)));
-        ema_accumulate_runs_kernel<true><<<dim3(gx, slices), ER_THREADS, er_smem_bytes<true>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats, flags);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, slices);
+        cfg.blockDim = dim3(ER_THREADS);
+        cfg.dynamicSmemBytes = er_smem_bytes<true>(K);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = flags ? 1 : 0;        // dependent of the tile-flag kernel: its slab initialisation overlaps that kernel
+        VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, ema_accumulate_runs_kernel<true>, x, idx, mask, N, int(D), T, K, stats,
+                                      (const unsigned char*)flags));
     } else if (K < (1 << 24) && D <= ErCfg<false>::DW) {
         static bool configured = false;
         if (!configured) {
