@@ -26,6 +26,8 @@ constexpr int ER_XS = ER_TT + 4;             // row stride (16-byte aligned rows
 constexpr int ER_WARPS = 16;                 // warp 15 sorts, warps 0..14 accumulate
 constexpr int ER_THREADS = ER_WARPS * 32;
 constexpr int ER_PER = (ER_TT + ER_WARPS - 2) / (ER_WARPS - 1);   // sorted rows per accumulating warp (5)
+constexpr int ER_LIST = 256;                 // valid tiles compacted per pass
+constexpr int ER_DYN_SMEM_MAX = 227 * 1024 - 4096;   // the kernel also has ~2.1 KB of static shared memory (4 KB with the reserved 1 KB, rounded)
 
 // flags[tile] = 1 when the 64-frame tile has at least one valid frame: padded tiles (35 % of an LJSpeech-like batch) are
 // then never loaded.  One warp per tile.
@@ -87,27 +89,60 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
         s_off[r] = d * ER_XS + t;
         t_of[r] = d < dn ? t : ER_TT;                               // depths beyond D are never copied (nor read)
     }
-    // tile -> (utterance, first frame), advanced incrementally (no 64-bit division in the loop)
-    const int64_t first = blockIdx.x, step = gridDim.x;
-    int64_t ld_tile = first;
-    int64_t ld_n = first / tiles_per_utt;
-    int ld_j = int(first % tiles_per_utt);
-    const int step_j = int(step % tiles_per_utt);
-    const int64_t step_n = step / tiles_per_utt;
     // launched as a programmatic dependent of ema_tile_flags_kernel: everything above overlapped it, the flags are read below
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    unsigned char ld_flag = (tile_flags && first < n_tiles) ? tile_flags[first] : 1;
 
-    auto issue = [&](int st) {
-        float* Xs = reinterpret_cast<float*>(stage0 + size_t(st) * STAGE_BYTES);
-        int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + DW * ER_XS);
-        float* s_mask = reinterpret_cast<float*>(s_idx + ER_TT);
-        if (ld_tile < n_tiles && ld_flag == 0) {
-            if (tid < ER_TT) { s_idx[tid] = -1; s_mask[tid] = 0.f; }      // nothing valid here: no rows, no loads
-        } else if (ld_tile < n_tiles) {
-            const int64_t t0 = int64_t(ld_j) * ER_TT;
+    // The CTA's tiles are first + k * step.  Only tiles with a valid frame enter the pipeline: warp 0 compacts them, up to
+    // ER_LIST at a time, into (utterance, tile-in-utterance) lists in shared memory.  (Walking padded tiles through the
+    // ring as empty copy groups left only ~26 KB of loads in flight per SM on a 35 %-padded batch: 1.5 TB/s.)
+    __shared__ int s_ln[ER_LIST], s_lj[ER_LIST];
+    __shared__ int s_nlist, s_scan;
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const int64_t n_mine = first < n_tiles ? (n_tiles - first + step - 1) / step : 0;      // tiles of this CTA
+    if (tid == 0) s_scan = 0;
+    auto build_list = [&]() {                       // warp 0 only; continues from candidate s_scan
+        int count = 0;
+        int64_t k = s_scan;
+        while (count <= ER_LIST - 32 && k < n_mine) {
+            const int64_t kk = k + lane;
+            const int64_t tile = first + kk * step;
+            const bool ok = kk < n_mine && (tile_flags == nullptr || tile_flags[tile] != 0);
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = count + __popc(m & ((1u << lane) - 1u));
+                s_ln[pos] = int(tile / tiles_per_utt);
+                s_lj[pos] = int(tile % tiles_per_utt);
+            }
+            count += __popc(m);
+            k += 32;
+        }
+        if (lane == 0) { s_nlist = count; s_scan = int(min(k, n_mine)); }
+    };
+
+    // group g of the pipeline = x tile g  +  indices/mask of tile g + 1 (the sorter needs those one iteration early, and
+    // keeping them out of their own tile's group lets STAGES - 2 tiles stay in flight instead of STAGES - 3)
+    auto issue_im = [&](int g, int n_list) {                                       // indices + mask of list entry g
+        if (g < n_list && tid < ER_TT) {
+            float* Xs = reinterpret_cast<float*>(stage0 + size_t(g % STAGES) * STAGE_BYTES);
+            int64_t* s_idx = reinterpret_cast<int64_t*>(Xs + DW * ER_XS);
+            float* s_mask = reinterpret_cast<float*>(s_idx + ER_TT);
+            const int64_t n = s_ln[g], t0 = int64_t(s_lj[g]) * ER_TT;
+            if (t0 + tid < T) {
+                cp_async8(s_idx + tid, idx + n * T + t0 + tid);
+                if (mask) cp_async4(s_mask + tid, mask + n * T + t0 + tid);
+                else s_mask[tid] = 1.f;
+            } else {
+                s_idx[tid] = -1;                   // frames beyond the utterance: no row (their x slots are never read)
+                s_mask[tid] = 0.f;
+            }
+        }
+    };
+    auto issue = [&](int g, int n_list) {
+        if (g < n_list) {
+            float* Xs = reinterpret_cast<float*>(stage0 + size_t(g % STAGES) * STAGE_BYTES);
+            const int64_t n = s_ln[g], t0 = int64_t(s_lj[g]) * ER_TT;
             const int tt = int(min(int64_t(ER_TT), T - t0));
-            const float* src = x + ld_n * int64_t(D) * T + t0;
+            const float* src = x + n * int64_t(D) * T + t0;
             if (vec16) {
 #pragma unroll
                 for (int r = 0; r < CHUNKS; ++r)
@@ -118,24 +153,9 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
                     if (t < tt) cp_async4(Xs + d * ER_XS + t, src + int64_t(d0 + d) * T + t);
                 }
             }
-            if (tid < ER_TT) {
-                if (tid < tt) {
-                    cp_async8(s_idx + tid, idx + ld_n * T + t0 + tid);
-                    if (mask) cp_async4(s_mask + tid, mask + ld_n * T + t0 + tid);
-                    else s_mask[tid] = 1.f;
-                } else {
-                    s_idx[tid] = -1;               // frames beyond the utterance: no row (their x slots are never read)
-                    s_mask[tid] = 0.f;
-                }
-            }
         }
+        issue_im(g + 1, n_list);
         cp_async_commit();
-        ld_tile += step;
-        ld_j += step_j;
-        ld_n += step_n;
-        if (ld_j >= tiles_per_utt) { ld_j -= tiles_per_utt; ++ld_n; }
-        // the flag of the tile after this one is fetched now and consumed by the next call (latency off the issue path)
-        ld_flag = (tile_flags && ld_tile < n_tiles) ? tile_flags[ld_tile] : 1;
     };
 
     // keys of a tile: (code << 8) | frame for valid rows, ~0u otherwise; 64 keys = 2 per lane, bitonic sort in one warp
@@ -174,60 +194,69 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
         out[32 + lane] = key[1];
     };
 
+    for (;;) {
+        __syncthreads();                               // previous list fully consumed (and s_scan initialised)
+        if (warp == 0) build_list();
+        __syncthreads();
+        const int n_list = s_nlist;
+        if (n_list == 0) break;
+        issue_im(0, n_list);
+        cp_async_commit();
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
-    cp_async_wait<STAGES - 2>();                   // tile 0 has landed
-    __syncthreads();
-    if (warp == ER_WARPS - 1) sort_tile(first < n_tiles, 0, sorted);
+        for (int g = 0; g < STAGES - 1; ++g) issue(g, n_list);
+        cp_async_wait<STAGES - 1>();                   // indices / mask of tile 0 have landed
+        __syncthreads();
+        if (warp == ER_WARPS - 1) sort_tile(true, 0, sorted);
 
-    int it = 0;
-    for (int64_t tile = first; tile < n_tiles; tile += step, ++it) {
-        cp_async_wait<STAGES - 3>();               // tiles it and it+1 have landed (this thread's copies)
-        __syncthreads();                           // ... everyone's; sorted[it & 1] is complete; stage of tile it-1 is free
-        issue((it + STAGES - 1) % STAGES);
-        if (warp == ER_WARPS - 1) {
-            sort_tile(tile + step < n_tiles, (it + 1) % STAGES, sorted + ((it + 1) & 1) * ER_TT);
-        } else {
-            const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(it % STAGES) * STAGE_BYTES);
-            const uint32_t* keys = sorted + (it & 1) * ER_TT;
-            const int lo = warp * ER_PER, hi = min(ER_TT, lo + ER_PER);
-            int i = lo;
-            const uint32_t kprev = (lo > 0 && lo < ER_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
-            // skip the tail of a run that started in an earlier warp's range
-            while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
-            while (i < hi) {
-                uint32_t key = keys[i];
-                if (key == 0xFFFFFFFFu) break;                                // sorted: no more rows
-                const uint32_t code = key >> 8;
-                float a[NQ];
+        for (int it = 0; it < n_list; ++it) {
+            cp_async_wait<STAGES - 2>();               // x of tile it and indices / mask of tile it+1 have landed (this thread's copies)
+            __syncthreads();                           // ... everyone's; sorted[it & 1] is complete; stage of tile it-1 is free
+            issue(it + STAGES - 1, n_list);
+            if (warp == ER_WARPS - 1) {
+                sort_tile(it + 1 < n_list, (it + 1) % STAGES, sorted + ((it + 1) & 1) * ER_TT);
+            } else {
+                const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(it % STAGES) * STAGE_BYTES);
+                const uint32_t* keys = sorted + (it & 1) * ER_TT;
+                const int lo = warp * ER_PER, hi = min(ER_TT, lo + ER_PER);
+                int i = lo;
+                const uint32_t kprev = (lo > 0 && lo < ER_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
+                // skip the tail of a run that started in an earlier warp's range
+                while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
+                while (i < hi) {
+                    uint32_t key = keys[i];
+                    if (key == 0xFFFFFFFFu) break;                                // sorted: no more rows
+                    const uint32_t code = key >> 8;
+                    float a[NQ];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) a[q] = 0.f;
-                float cnt = 0.f;
-                do {                                                          // one run; may continue past hi
-                    const float* col = Xs + (key & 255u);
+                    for (int q = 0; q < NQ; ++q) a[q] = 0.f;
+                    float cnt = 0.f;
+                    do {                                                          // one run; may continue past hi
+                        const float* col = Xs + (key & 255u);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        if (lane + 32 * q < dn) a[q] += col[(lane + 32 * q) * ER_XS];
-                    cnt += 1.f;
-                    ++i;
-                    key = i < ER_TT ? keys[i] : 0xFFFFFFFFu;
-                } while (key != 0xFFFFFFFFu && (key >> 8) == code);
+                        for (int q = 0; q < NQ; ++q)
+                            if (lane + 32 * q < dn) a[q] += col[(lane + 32 * q) * ER_XS];
+                        cnt += 1.f;
+                        ++i;
+                        key = i < ER_TT ? keys[i] : 0xFFFFFFFFu;
+                    } while (key != 0xFFFFFFFFu && (key >> 8) == code);
 #if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 256)      /* timing experiment: no updates */
-                if (a[0] + cnt == -12345.f) sums[0] = 1.f;
+                    if (a[0] + cnt == -12345.f) sums[0] = 1.f;
 #else
-                if (SLAB) {
+                    if (SLAB) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) slab[size_t(code) * DW + lane + 32 * q] += a[q];
-                    if (count_here && lane == 0) scnt[code] += cnt;
-                } else {
+                        for (int q = 0; q < NQ; ++q) slab[size_t(code) * DW + lane + 32 * q] += a[q];
+                        if (count_here && lane == 0) scnt[code] += cnt;
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        if (lane + 32 * q < dn) atomicAdd(&sums[size_t(code) * D + lane + 32 * q], a[q]);
-                    if (lane == 0) atomicAdd(&counts[code], cnt);
-                }
+                        for (int q = 0; q < NQ; ++q)
+                            if (lane + 32 * q < dn) atomicAdd(&sums[size_t(code) * D + lane + 32 * q], a[q]);
+                        if (lane == 0) atomicAdd(&counts[code], cnt);
+                    }
 #endif
+                }
             }
         }
+        cp_async_wait<0>();                            // (only empty groups are left)
     }
     cp_async_wait<0>();
     if (SLAB) {

@@ -276,11 +276,11 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
         ema_tile_flags_kernel<<<unsigned((tiles_r * 32 + 255) / 256), 256, 0, stream>>>(mask, N, T, tpu, flags);
         VQ_CUDA_OK(cudaGetLastError());
     }
-    if (K < (1 << 24) && er_smem_bytes<true>(K) <= 227 * 1024) {
+    if (K < (1 << 24) && er_smem_bytes<true>(K) <= ER_DYN_SMEM_MAX) {
         // private [K][64] slab per (row chunk, 64-deep slice); one CTA per SM
         static bool configured = false;
         if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ER_DYN_SMEM_MAX));
             configured = true;
         }
         const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
@@ -300,7 +300,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
     } else if (K < (1 << 24) && D <= ErCfg<false>::DW) {
         static bool configured = false;
         if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ER_DYN_SMEM_MAX));
             configured = true;
         }
         const int grid = int(std::min<int64_t>(tiles_r, num_sms()));
