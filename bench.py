@@ -281,9 +281,29 @@ def run_b200(args):
     fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
     blk.rng_parity = False                   # restart rows drawn on the device: no host sync, no CPU randperm
     fwd_fast_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
+    # the same forward replayed from a CUDA graph (no host launch cost; static input addresses, as any graphed module)
+    fwd_graph_ms = None
+    try:
+        if world > 1:
+            raise RuntimeError("single-GPU only (the forward contains an NCCL all-reduce when world_size > 1)")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                blk(xd, md_all, update_k=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            g_out = blk(xd, md_all, update_k=True)
+        fwd_graph_ms = timed_all(graph.replay)
+        del graph, g_out
+    except Exception as exc:                                  # noqa: BLE001  (reported, never fatal for the bench line)
+        fwd_graph_ms = None
+        graph_error = repr(exc)[:200]
     del blk
 
-    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms, fwd_graph_ms if fwd_graph_ms else 0.0], dtype=torch.float64, device=dev)
     frames = torch.tensor([float(valid_frames), float(rows)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, dist.ReduceOp.MAX)
@@ -292,7 +312,7 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    ms, e2e_ms, fwd_ms, fwd_fast_ms = float(times[0]), float(times[1]), float(times[2]), float(times[3])
+    ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms = (float(times[i]) for i in range(5))
     tot_valid, tot_rows = float(frames[0]), float(frames[1])
     value = tot_valid * args.steps / (ms * 1e-3)
     e2e_value = tot_valid * args.steps / (e2e_ms * 1e-3)
@@ -381,6 +401,9 @@ def run_b200(args):
                                      "note": "whole nn.Module training forward per rank (K1+K2+K3a+all-reduce+K3b+restart-row glue), max over ranks"}
     other["module_forward_train_device_rng"] = {"ms": fwd_fast_ms, "valid_frames_per_s": tot_valid / (fwd_fast_ms * 1e-3),
                                                 "note": "same with rng_parity=False (restart rows drawn on the device, no host sync)"}
+    if fwd_graph_ms:
+        other["module_forward_train_cuda_graph"] = {"ms": fwd_graph_ms, "valid_frames_per_s": tot_valid / (fwd_graph_ms * 1e-3),
+                                                    "note": "rng_parity=False forward captured once with torch.cuda.graph and replayed"}
 
     cpu, cores, sample_desc = cpu_reference_rate(budget_s=16.0)
     line = {

@@ -151,6 +151,16 @@ int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old,
 int vq_gather_rows(const float* x, const int64_t* rows, int64_t n_rows, int64_t n_utt, int64_t emb_width,
                    int64_t t_frames, float* out, void* stream);
 
+/* Device-side variant of the restart-row draw (no host round trip, different random stream than the reference:
+ * BottleneckBlock(rng_parity=False)): out[j,:] = x[n_j,:,t_j] for k_bins frames drawn uniformly, with replacement, among
+ * the frames with mask != 0 (all frames when mask is NULL) -- the distribution of y[randperm(M)][:K] (bottleneck.py:40,70)
+ * up to repeats.  When there are fewer valid frames than codes the rows get the N(0, (0.01/sqrt(D))^2) jitter of `_tile`
+ * (bottleneck.py:26-33); with no valid frame at all they are zero.  The counter-based stream is selected by
+ * seed ^ *seed_dev (seed_dev: optional device word, e.g. a call counter the caller increments on the device so that a
+ * captured CUDA graph draws fresh rows on every replay); scratch: (n_utt + 1) * 8 bytes of device memory. */
+int vq_restart_rows_device(const float* x, const float* mask, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+                           int k_bins, uint64_t seed, const uint64_t* seed_dev, float* out, void* scratch, void* stream);
+
 /* Optional per-kernel timing of vq_assign with CUDA events recorded on the launching stream (what bench.py's
  * roofline uses).  vq_profile_enable(1) clears the ring and starts recording the next (up to 64) calls;
  * vq_profile_read synchronises on the last recorded event and writes the AVERAGE milliseconds per call of

@@ -42,6 +42,8 @@ SIGNATURES = {
     "vq_ema_finalize": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                  _c_double, _c_double, _c_double, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "vq_gather_rows": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_void_p, _c_void_p]),
+    "vq_restart_rows_device": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_uint64, _c_void_p, _c_void_p,
+                                        _c_void_p, _c_void_p]),
     "vq_profile_enable": (_c_int, [_c_int]),
     "vq_profile_read": (_c_int, [_c_void_p]),
     "vq_host_ctx_create": (_c_void_p, [_c_int, _c_i64, _c_int, _c_int]),

@@ -411,4 +411,110 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* _
     for (int d = threadIdx.x; d < D; d += blockDim.x) out[j * D + d] = src[int64_t(d) * T];
 }
 
+
+// ---- device-side restart rows (vq_restart_rows_device): valid frames per utterance -> prefix sums -> K uniform draws
+__global__ void __launch_bounds__(256) restart_count_kernel(const float* __restrict__ mask, int64_t N, int64_t T,
+                                                           long long* __restrict__ prefix) {
+    const int64_t n = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;          // one warp per utterance
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    long long c = 0;
+    if (mask == nullptr) c = lane == 0 ? T : 0;
+    else for (int64_t t = lane; t < T; t += 32) c += mask[n * T + t] != 0.f ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) prefix[n + 1] = c;
+    if (n == 0 && lane == 0) prefix[0] = 0;
+}
+// in-place inclusive scan of prefix[1..N] by one block
+__global__ void __launch_bounds__(1024) restart_scan_kernel(long long* __restrict__ prefix, int64_t N) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < N; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        long long v = i < N ? prefix[i + 1] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? warp_tot[warp - 1] : 0);
+        if (i < N) prefix[i + 1] = v + before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// one block per drawn row
+__global__ void __launch_bounds__(128) restart_select_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                            const long long* __restrict__ prefix, int64_t N, int D, int64_t T,
+                                                            int K, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                                            float* __restrict__ out) {
+    __shared__ long long s_src;               // offset of x[n, 0, t], or -1
+    const int j = blockIdx.x, lane = threadIdx.x & 31;
+    if (seed_dev) seed ^= splitmix64(*seed_dev);
+    const long long m = prefix[N];
+    if (threadIdx.x < 32) {
+        long long src = -1;
+        if (m > 0) {
+            const uint64_t h = splitmix64(seed ^ (uint64_t(j) * 0xD1342543DE82EF95ull));
+            long long r = (long long)(__umul64hi(h, uint64_t(m)));                // uniform in [0, m)
+            int64_t lo = 0, hi = N;                                               // utterance n: prefix[n] <= r < prefix[n+1]
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (prefix[mid] <= r) lo = mid; else hi = mid;
+            }
+            const int64_t n = lo;
+            long long q = r - prefix[n];                                          // q-th valid frame of utterance n
+            int64_t t_found = -1;
+            if (mask == nullptr) t_found = q;
+            else {
+                for (int64_t t0 = 0; t0 < T && t_found < 0; t0 += 32) {
+                    const bool v = t0 + lane < T && mask[n * T + t0 + lane] != 0.f;
+                    const unsigned b = __ballot_sync(0xffffffffu, v);
+                    const int c = __popc(b);
+                    if (q < c) t_found = t0 + __fns(b, 0, int(q) + 1);
+                    else q -= c;
+                }
+            }
+            if (t_found >= 0) src = n * int64_t(D) * T + t_found;
+        }
+        if (lane == 0) s_src = src;
+    }
+    __syncthreads();
+    const long long src = s_src;
+    const float jitter = m < K ? 0.01f * rsqrtf(float(D)) : 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float v = src >= 0 ? x[src + int64_t(d) * T] : 0.f;
+        if (jitter != 0.f && src >= 0) {                                          // Box-Muller on two hashed uniforms
+            const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(j) * uint64_t(D) + uint64_t(d) + 0x5851F42D4C957F2Dull));
+            const float u1 = (float(uint32_t(h >> 40)) + 1.f) * (1.f / 16777217.f);
+            const float u2 = float(uint32_t(h) >> 8) * (1.f / 16777216.f);
+            v += jitter * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+        }
+        out[size_t(j) * D + d] = v;
+    }
+}
+
 }  // namespace vq

@@ -333,6 +333,26 @@ int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old,
     return 0;
 }
 
+int vq_restart_rows_device(const float* x, const float* mask, int64_t N, int64_t D, int64_t T, int K, uint64_t seed,
+                           const uint64_t* seed_dev, float* out, void* scratch, void* stream_) {
+    if (check_shape(N, D, T, K)) return 1;
+    VQ_REQUIRE(x && out && scratch, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    long long* prefix = static_cast<long long*>(scratch);
+    if (N == 0 || T == 0) {
+        VQ_CUDA_OK(cudaMemsetAsync(out, 0, size_t(K) * D * sizeof(float), stream));
+        return 0;
+    }
+    restart_count_kernel<<<unsigned((N * 32 + 255) / 256), 256, 0, stream>>>(mask, N, T, prefix);
+    VQ_CUDA_OK(cudaGetLastError());
+    restart_scan_kernel<<<1, 1024, 0, stream>>>(prefix, N);
+    VQ_CUDA_OK(cudaGetLastError());
+    restart_select_kernel<<<K, 128, 0, stream>>>(x, mask, prefix, N, int(D), T, K, seed, seed_dev, out);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int vq_gather_rows(const float* x, const int64_t* rows, int64_t n_rows, int64_t N, int64_t D, int64_t T, float* out,
                    void* stream) {
     if (n_rows == 0) return 0;

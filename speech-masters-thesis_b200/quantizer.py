@@ -117,6 +117,25 @@ def gather_rows(x, rows):
     return out
 
 
+def restart_rows_device(x, mask, k_bins, counter):
+    """K rows of the NCT tensor x drawn uniformly (with replacement) among the frames with mask != 0, on the device.
+    `counter` is a 1-element int64 CUDA tensor; it selects the random stream together with torch.initial_seed() and is
+    incremented here (on the device), so consecutive calls -- and consecutive replays of a captured graph -- differ."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n, d, t = x.shape
+    out = torch.empty((k_bins, d), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(n + 1, dtype=torch.int64, device=x.device)
+    m = mask.reshape(n, t) if mask is not None else None
+    if m is not None and (m.dtype != torch.float32 or not m.is_contiguous()):
+        m = m.to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.vq_restart_rows_device(ptr(x), ptr(m), n, d, t, k_bins, torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, ptr(counter),
+                                         ptr(out), ptr(scratch), _stream(x)), "vq_restart_rows_device")
+    counter.add_(1)
+    return out
+
+
 class _QuantizeST(torch.autograd.Function):
     """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
 
@@ -176,6 +195,13 @@ class BottleneckBlock(nn.Module):
         self.reset_k()
 
     # ---- state (bottleneck.py:20-24)
+    def _device_rng_counter(self, device):
+        c = getattr(self, "_rng_counter", None)
+        if c is None or c.device != device:
+            c = torch.zeros(1, dtype=torch.int64, device=device)
+            self._rng_counter = c
+        return c
+
     def reset_k(self):
         self.init = False
         self.k_sum = None
@@ -199,16 +225,8 @@ class BottleneckBlock(nn.Module):
         n, d, t = x.shape
         flat = mask.reshape(-1) if mask is not None else None
         if not self.rng_parity:
-            # device-only: the r-th valid frame for K uniform ranks r, via a prefix sum of the mask (no host sync)
-            valid = (flat != 0) if flat is not None else torch.ones(n * t, dtype=torch.bool, device=x.device)
-            csum = torch.cumsum(valid, 0)
-            m = csum[-1]
-            ranks = (torch.rand(self.k_bins, device=x.device) * m).long().clamp_(min=0)
-            ranks = torch.minimum(ranks, (m - 1).clamp_(min=0))
-            pos = torch.searchsorted(csum, ranks + 1).clamp_(max=n * t - 1)
-            rows = gather_rows(x, pos)
-            jitter = (m < self.k_bins).to(rows.dtype) * (0.01 / math.sqrt(d))      # the reference's _tile noise, only when rows repeat
-            return rows + torch.randn_like(rows) * jitter
+            # device-only (vq_restart_rows_device): K uniform draws among the valid frames, no host sync, graph-capturable
+            return restart_rows_device(x, mask, self.k_bins, self._device_rng_counter(x.device))
         valid_pos = (torch.nonzero(flat != 0)[:, 0] if flat is not None
                      else torch.arange(n * t, device=x.device))          # host sync (the reference has three)
         m = valid_pos.numel()

@@ -463,3 +463,38 @@ def test_three_accumulator_stage_mode(vq, monkeypatch):
     monkeypatch.delenv("VQ_K1_STAGES")
     assert torch.equal(base, three)
     check_indices(rows, code, o_l, three)
+
+
+def test_restart_rows_device_entry_point(vq):
+    """vq_restart_rows_device: every drawn row is a valid frame of the batch; all valid frames are reachable; fewer valid
+    frames than codes -> jittered copies; no valid frame -> zeros; a NULL mask means every frame is valid."""
+    from importlib import import_module
+    q = import_module(vq.__name__ + ".quantizer")
+    gen = torch.Generator().manual_seed(3)
+    n, d, t, K = 5, 24, 96, 4096
+    x = torch.randn(n, d, t, generator=gen)
+    lengths = torch.tensor([96, 50, 1, 0, 33])
+    mask = (torch.arange(t)[None, :] < lengths[:, None]).float().view(n, 1, t)
+    mask[0, 0, 10:20] = 0.0                                   # holes: the mask is not a prefix mask
+    rows, _, valid = O.flatten_nct(x, mask)
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    out = q.restart_rows_device(x.to(DEV), mask.to(DEV), K, counter).cpu()
+    assert int(counter) == 1
+    vrows = rows[valid]
+    match = (out[:, None, :] == vrows[None, :, :]).all(dim=2)        # [K, M]
+    assert bool(match.any(dim=1).all())                              # every draw is a valid frame, bit for bit
+    assert bool(match.any(dim=0).all())                              # 4096 draws over 170 frames: each one is hit
+    counts = match.float().sum(dim=0)
+    assert float(counts.max()) < 4.0 * K / vrows.shape[0]            # roughly uniform
+    out2 = q.restart_rows_device(x.to(DEV), mask.to(DEV), K, counter).cpu()
+    assert not torch.equal(out, out2)                                # the counter moved the stream
+    few = torch.zeros_like(mask)
+    few[1, 0, :3] = 1.0                                              # 3 valid frames < 64 codes: jittered copies
+    j = q.restart_rows_device(x.to(DEV), few.to(DEV), 64, counter).cpu()
+    base = O.flatten_nct(x, few)[0][O.flatten_nct(x, few)[2]]
+    dist = (j[:, None, :] - base[None, :, :]).abs().amax(dim=2).min(dim=1).values
+    assert float(dist.max()) < 0.05 and float(dist.min()) > 0.0
+    none = q.restart_rows_device(x.to(DEV), torch.zeros_like(mask).to(DEV), 8, counter).cpu()
+    assert float(none.abs().max()) == 0.0
+    allv = q.restart_rows_device(x.to(DEV), None, 256, counter).cpu()
+    assert bool((allv[:, None, :] == rows[None, :, :]).all(dim=2).any(dim=1).all())
