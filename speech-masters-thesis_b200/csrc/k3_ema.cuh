@@ -277,6 +277,10 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
 //  against 0.115 ms for the kernel above.  With idle consumers the same ring streams the valid tiles in 0.068 ms, i.e.
 //  2.8 TB/s: 64-frame tiles of a 64-deep slice are 256-byte pieces at a stride of T*4 bytes, which is what bounds both.)
 
+// (Also tried and measured, not kept: the whole shared memory as a six-stage TMA ring, two consumer warps per stage, groups
+//  of equal codes found with match.any and flushed as coalesced 128-byte reductions straight to L2 instead of a slab:
+//  0.139 ms -- 1.15 M vector reductions to 512 hot rows cost more than the shared-memory slab saves.)
+
 // Large-K variant: rows of one tile rarely share a code, so privatisation buys nothing; transpose the
 // tile through shared memory and issue depth-coalesced FP32 reductions straight to L2.
 __global__ void __launch_bounds__(E_THREADS)

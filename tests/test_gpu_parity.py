@@ -471,23 +471,26 @@ def test_restart_rows_device_entry_point(vq):
     from importlib import import_module
     q = import_module(vq.__name__ + ".quantizer")
     gen = torch.Generator().manual_seed(3)
-    n, d, t, K = 5, 24, 96, 4096
+    n, d, t, K = 5, 24, 96, 160
     x = torch.randn(n, d, t, generator=gen)
     lengths = torch.tensor([96, 50, 1, 0, 33])
     mask = (torch.arange(t)[None, :] < lengths[:, None]).float().view(n, 1, t)
     mask[0, 0, 10:20] = 0.0                                   # holes: the mask is not a prefix mask
     rows, _, valid = O.flatten_nct(x, mask)
+    vrows = rows[valid]                                       # 170 valid frames >= K: no jitter, draws are exact copies
     counter = torch.zeros(1, dtype=torch.int64, device=DEV)
-    out = q.restart_rows_device(x.to(DEV), mask.to(DEV), K, counter).cpu()
-    assert int(counter) == 1
-    vrows = rows[valid]
-    match = (out[:, None, :] == vrows[None, :, :]).all(dim=2)        # [K, M]
-    assert bool(match.any(dim=1).all())                              # every draw is a valid frame, bit for bit
-    assert bool(match.any(dim=0).all())                              # 4096 draws over 170 frames: each one is hit
-    counts = match.float().sum(dim=0)
-    assert float(counts.max()) < 4.0 * K / vrows.shape[0]            # roughly uniform
-    out2 = q.restart_rows_device(x.to(DEV), mask.to(DEV), K, counter).cpu()
-    assert not torch.equal(out, out2)                                # the counter moved the stream
+    hits = torch.zeros(vrows.shape[0])
+    outs = []
+    for _ in range(24):
+        out = q.restart_rows_device(x.to(DEV), mask.to(DEV), K, counter).cpu()
+        match = (out[:, None, :] == vrows[None, :, :]).all(dim=2)    # [K, M]
+        assert bool(match.any(dim=1).all())                          # every draw is a valid frame, bit for bit
+        hits += match.float().sum(dim=0)
+        outs.append(out)
+    assert int(counter) == 24
+    assert float(hits.min()) > 0                                     # 3840 draws over 170 frames: each one is hit
+    assert float(hits.max()) < 3.0 * 24 * K / vrows.shape[0]         # roughly uniform
+    assert not torch.equal(outs[0], outs[1])                         # the counter moved the stream
     few = torch.zeros_like(mask)
     few[1, 0, :3] = 1.0                                              # 3 valid frames < 64 codes: jittered copies
     j = q.restart_rows_device(x.to(DEV), few.to(DEV), 64, counter).cpu()
