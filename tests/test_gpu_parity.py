@@ -501,3 +501,71 @@ def test_restart_rows_device_entry_point(vq):
     assert float(none.abs().max()) == 0.0
     allv = q.restart_rows_device(x.to(DEV), None, 256, counter).cpu()
     assert bool((allv[:, None, :] == rows[None, :, :]).all(dim=2).any(dim=1).all())
+
+
+def test_ema_accumulate_many_tiles_per_block(vq):
+    """More than 256 valid 64-frame tiles per thread block: the accumulate kernel compacts its valid tiles into a
+    shared-memory list of 256 entries and must walk through several lists (incl. a ragged last one and padded tiles)."""
+    lib = vq._lib.load()
+    gen = torch.Generator().manual_seed(11)
+    n, d, t, K = 304, 128, 4096, 64                       # 304 * 64 tiles = 19456 > 74 blocks * 256
+    x = torch.randn(n, d, t, generator=gen, dtype=torch.float32).to(DEV)
+    idx = torch.randint(0, K, (n, t), generator=gen).to(DEV)
+    lengths = torch.randint(1, t + 1, (n,), generator=gen)
+    lengths[::7] = t
+    lengths[3::11] = 0                                    # whole utterances of padding
+    mask = (torch.arange(t)[None, :] < lengths[:, None]).float().to(DEV)
+    stats = torch.zeros(K * d + K, device=DEV)
+    scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=DEV)
+    rc = lib.vq_ema_accumulate(x.data_ptr(), idx.data_ptr(), mask.data_ptr(), n, d, t, K, stats.data_ptr(), scratch.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.vq_last_error()
+    sel = mask.reshape(-1) != 0
+    flat = x.permute(0, 2, 1).reshape(-1, d)
+    ref = torch.zeros(K, d, device=DEV, dtype=torch.float64).index_add_(0, idx.reshape(-1)[sel], flat[sel].double())
+    cnt = torch.bincount(idx.reshape(-1)[sel], minlength=K).float()
+    assert torch.equal(stats[K * d:], cnt)
+    close(stats[:K * d].view(K, d), ref.float(), rtol=2e-4, atol=2e-2)     # sums of ~10^4 N(0,1) terms in FP32
+
+
+def test_training_forward_in_a_cuda_graph(vq):
+    """rng_parity=False makes the training forward free of host synchronisation: it can be captured once and replayed;
+    every replay updates the codebook like an eager call on the same input would."""
+    gen = torch.Generator().manual_seed(21)
+    K, D = 128, 64
+    code = torch.randn(K, D, generator=gen)
+    lengths = torch.tensor([256, 200, 131, 64])
+    x, mask = O.synthetic_batch(lengths, D, gen, codebook=code)
+    xd, md = x.to(DEV), mask.to(DEV)
+
+    def fresh():
+        blk = vq.BottleneckBlock(K, D, 0.99, 1.0, rng_parity=False).to(DEV)
+        blk.k, blk.k_sum, blk.k_elem, blk.init = code.to(DEV).clone(), code.to(DEV).clone(), torch.ones(K, device=DEV), True
+        blk.train()
+        return blk
+
+    eager = fresh()
+    with torch.no_grad():
+        e_l, e_q, e_commit, e_metrics = eager(xd, md, update_k=True)
+    blk = fresh()
+    static_k = blk.k
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        warm = fresh()
+        for _ in range(2):
+            warm(xd, md, update_k=True)                   # allocates the cached workspaces outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(graph):
+        g_l, g_q, g_commit, g_metrics = blk(xd, md, update_k=True)
+    blk.k = static_k                                      # replay reads the codebook it was captured with
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g_l.cpu(), e_l.cpu())
+    assert torch.equal(g_q.cpu(), e_q.cpu())
+    close(g_commit, e_commit)
+    assert float(g_metrics["usage"]) == float(e_metrics["usage"])
+    assert int(g_metrics["used_curr"]) == int(e_metrics["used_curr"])
+    close(g_metrics["entropy"], e_metrics["entropy"])
