@@ -64,10 +64,17 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
         __syncthreads();
         if (VEC) {
             constexpr int ES = G_TT + 4;
-            // ---- gather: one warp per frame, coalesced reads of the codebook row, transposed into Es[depth][frame]
-            for (int r = warp; r < tt; r += G_THREADS / 32) {
-                const float* src = k + size_t(s_idx[r]) * D;
-                for (int d = lane; d < D; d += 32) Es[d * ES + r] = __ldg(src + d);
+            // ---- gather, transposed into Es[depth][frame]: a warp copies 4 codebook rows x 8 depths per instruction
+            // (lane = 4 * depth + row), so the 32 stores of an instruction fall into 32 different banks (row stride 68)
+            {
+                const int rr = lane & 3, dd = lane >> 2;
+                for (int r4 = warp * 4; r4 < tt; r4 += (G_THREADS / 32) * 4) {
+                    const int r = r4 + rr;                                       // (tt is a multiple of 4 on this path)
+                    const float* src = k + size_t(s_idx[r]) * D + dd;
+                    float* dst = Es + dd * ES + r;
+#pragma unroll 4
+                    for (int d8 = 0; d8 + dd < D; d8 += 8) dst[d8 * ES] = __ldg(src + d8);
+                }
             }
             __syncthreads();
             // ---- stream: G_TT/4 threads cover the frames of one depth with float4
