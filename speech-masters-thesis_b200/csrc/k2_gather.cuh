@@ -19,12 +19,13 @@ enum GatherMode { GM_FWD = 0, GM_BWD = 1, GM_DECODE = 2 };
 //   VEC = true : Es[depth][G_TT + 4], 16-byte accesses along frames (T % 4 == 0, 16-byte aligned tensors): a warp moves
 //                512 contiguous bytes per request and a thread has 8 independent 16-byte loads in flight.
 template <int MODE, bool VEC>
-__global__ void __launch_bounds__(G_THREADS, VEC ? 4 : 6)      // the kernel is latency-bound: 6 resident CTAs (40 registers) beat 5
+__global__ void __launch_bounds__(G_THREADS, (VEC || MODE == GM_DECODE) ? 4 : 6)   // forward/backward: latency-bound, 6 resident CTAs (40 registers) beat 5;
+                                                                                   // decode keeps 32 gathered values in registers instead
 gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
               const float* __restrict__ k, const float* __restrict__ grad_xq, const float* __restrict__ grad_commit,
               int64_t N, int D, int64_t T, int K, int Ds,
               float* __restrict__ out, double* __restrict__ scalars, float* __restrict__ results,
-              unsigned int total_blocks) {
+              unsigned int total_blocks, int dec4) {
     extern __shared__ __align__(16) float smem[];
     float* Es = smem;                                   // [G_TT][Ds] or [D][G_TT + 4]
     const size_t es_floats = ((VEC ? size_t(D) * (G_TT + 4) : size_t(G_TT) * Ds) + 3) & ~size_t(3);
@@ -45,22 +46,33 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
     }
     double sq = 0.0, sq_all = 0.0, msum_local = 0.0;
 
+    // index and mask of frame `tid` of a tile, loaded one tile ahead (they stream from HBM: a synchronous load would put a
+    // DRAM round trip into every tile of every block)
+    int64_t pre_ci = 0;
+    float pre_m = 0.f;
+    auto load_im = [&](int64_t tile) {
+        pre_ci = 0; pre_m = 0.f;
+        if (tid < G_TT && tile < n_tiles) {
+            const int64_t n = tile / tiles_per_utt, t = (tile % tiles_per_utt) * G_TT + tid;
+            if (t < T) {
+                pre_ci = idx[n * T + t];
+                pre_m = mask ? mask[n * T + t] : 1.f;
+            }
+        }
+    };
+    constexpr bool PREFETCH = MODE == GM_DECODE;       // (measured: the extra registers cost the 40-register forward/backward more than they save)
+    if (PREFETCH) load_im(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t n = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * G_TT;
         const int tt = int(min(int64_t(G_TT), T - t0));
         __syncthreads();
+        if (!PREFETCH) load_im(tile);
         if (tid < G_TT) {
-            int c = 0;
-            float m = 0.f;
-            if (tid < tt) {
-                int64_t ci = idx[n * T + t0 + tid];
-                c = int(min(max(ci, int64_t(0)), int64_t(K - 1)));
-                m = mask ? mask[n * T + t0 + tid] : 1.f;
-            }
-            s_idx[tid] = c;
-            s_mask[tid] = m;
-            if (MODE == GM_FWD) msum_local += double(m);
+            s_idx[tid] = int(min(max(pre_ci, int64_t(0)), int64_t(K - 1)));
+            s_mask[tid] = pre_m;
+            if (MODE == GM_FWD) msum_local += double(pre_m);
         }
+        if (PREFETCH) load_im(tile + gridDim.x);
         __syncthreads();
         if (VEC) {
             constexpr int ES = G_TT + 4;
@@ -127,13 +139,46 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, cons
                 sq += double(acc_valid);
             }
         } else {
-            // ---- gather: one warp per row, coalesced 128-byte reads of the codebook row (L2-resident)
-            for (int r = warp; r < tt; r += G_THREADS / 32) {
-                const float* src = k + size_t(s_idx[r]) * D;
-                float* dst = Es + size_t(r) * Ds;
-                for (int d = lane; d < D; d += 32) dst[d] = __ldg(src + d);
+            // ---- gather: one warp per row, coalesced 128-byte reads of the codebook row (L2-resident).  Decode, D <= 128: all
+            // the loads of a warp's 8 rows are issued before the first store (one L2 round trip per tile instead of eight).
+            if (MODE == GM_DECODE && D <= 128) {
+                float v[G_TT / (G_THREADS / 32)][4];
+#pragma unroll
+                for (int i = 0; i < G_TT / (G_THREADS / 32); ++i) {
+                    const int r = warp + i * (G_THREADS / 32);
+                    const float* src = k + size_t(s_idx[r]) * D;              // (rows beyond tt hold code 0: harmless reads)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[i][q] = lane + 32 * q < D ? __ldg(src + lane + 32 * q) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < G_TT / (G_THREADS / 32); ++i) {
+                    float* dst = Es + size_t(warp + i * (G_THREADS / 32)) * Ds;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < D) dst[lane + 32 * q] = v[i][q];
+                }
+            } else {
+                for (int r = warp; r < tt; r += G_THREADS / 32) {
+                    const float* src = k + size_t(s_idx[r]) * D;
+                    float* dst = Es + size_t(r) * Ds;
+                    for (int d = lane; d < D; d += 32) dst[d] = __ldg(src + d);
+                }
             }
             __syncthreads();
+            if (MODE == GM_DECODE && dec4) {
+                // decode with 16-byte stores (T % 4 == 0, aligned output): a thread owns 4 consecutive frames and walks the
+                // depth; 4 shared-memory reads (2-way conflicts) + 1 store per 4 elements.  The 4-byte loop below spent
+                // ~26 thread instructions per element and was issue-bound (69 % issue utilisation, DRAM 34 % busy).
+                const int t4 = (tid & 15) * 4, dg = tid >> 4;             // 16 frame quads x 16 depth groups
+                if (t4 < tt) {
+                    const float* e0 = Es + size_t(t4) * Ds;
+                    float* dst = out + (size_t(n) * D) * T + t0 + t4;
+#pragma unroll 4
+                    for (int d = dg; d < D; d += G_THREADS / 16)
+                        st_stream4(reinterpret_cast<float4*>(dst + size_t(d) * T), make_float4(e0[d], e0[Ds + d], e0[2 * Ds + d], e0[3 * Ds + d]));
+                }
+                continue;
+            }
             // ---- stream: lanes along frames (coalesced), warps along depth
             const int t = tid & (G_TT - 1);
             const int dgrp = tid / G_TT;                       // 0..3

@@ -42,8 +42,9 @@ static int launch_gather_v(const float* x, const int64_t* idx, const float* mask
     int64_t tiles = N * ((T + G_TT - 1) / G_TT);
     int per_sm = std::max(1, std::min(8, (220 * 1024) / (smem + 1024)));
     int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * per_sm));
+    const int dec4 = (MODE == GM_DECODE && T % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     gather_kernel<MODE, VEC><<<grid, G_THREADS, smem, stream>>>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, Ds, out,
-                                                                scalars, results, (unsigned int)grid);
+                                                                scalars, results, (unsigned int)grid, dec4);
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }
