@@ -171,8 +171,12 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
             const int64_t ci = s_idx[t];
             key[r] = (s_mask[t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
         }
+#if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 2048)     /* timing experiment: no sorting network (wrong results) */
+        for (int k = 2; k <= 0; k <<= 1) {
+#else
 #pragma unroll
         for (int k = 2; k <= ER_TT; k <<= 1) {
+#endif
 #pragma unroll
             for (int j = k >> 1; j > 0; j >>= 1) {
                 if (j >= 32) {                     // j == 32, k == 64: partner is the lane's other key, ascending
