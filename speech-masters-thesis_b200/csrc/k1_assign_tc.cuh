@@ -75,7 +75,6 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
-    uint32_t key_mul;        // 64, passed at run time so the key is ONE integer multiply-add
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -237,7 +236,6 @@ struct KeySpace {
     float offset;        // B
     float half_range;    // 2^(E-1)
     float ulp;           // 2^(E-23): spacing of t
-    uint32_t top6;       // the six bits of bits(t) the key drops (sign + five exponent MSBs; identical for every t)
 };
 __device__ __forceinline__ KeySpace make_key_space(float e_norm_max) {
     KeySpace ks;
@@ -249,12 +247,13 @@ __device__ __forceinline__ KeySpace make_key_space(float e_norm_max) {
     ks.half_range = ldexpf(1.f, e);
     ks.offset = ldexpf(1.5f, e + 1);
     ks.ulp = ldexpf(1.f, e + 1 - 23);
-    ks.top6 = __float_as_uint(ks.offset) & 0xFC000000u;
     return ks;
 }
-__device__ __forceinline__ float key_to_t(uint32_t key, uint32_t top6) { return __uint_as_float((key >> 6) | top6); }
 
-// Best and runner-up of 64 keys in ~1.2 integer min/max per code (the ALU pipe is what bounds this kernel at small D).
+// Best and runner-up of 64 scores in ~1.2 integer min/max per code and nothing else: the keys are the raw bits of t (no
+// column packed in).  The winner's column is recovered from the two families instead: its block from the block maxima
+// (tracked per half tile), its residue from the chain that holds the overall maximum (found once per frame); a tie in
+// either makes runner-up == best, i.e. an unsafe frame, so a safe frame always has a unique (block, residue) = column.
 // Every column belongs to two families of running maxima: its RESIDUE chain (column mod 16, ch[16], kept over all the
 // code tiles a scan group visits) and its BLOCK (16 consecutive columns).  A (residue, block) cell holds exactly one
 // column, so any code other than the winner differs from it in residue or in block, and
@@ -263,8 +262,8 @@ __device__ __forceinline__ float key_to_t(uint32_t key, uint32_t top6) { return 
 // a direct scan is only paid per block (here, t1/t2 = top-2 over the four block maxima) and once per frame for the chains.
 // MODE 0: hn_off in global memory, 1: in shared memory, 2: folded into the accumulator by the MMA (no subtraction at all).
 template <int MODE>
-__device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float* hn_off, uint32_t key_mul,
-                                       uint32_t (&ch)[16], uint32_t& t1, uint32_t& t2) {
+__device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float* hn_off,
+                                       uint32_t (&ch)[16], uint32_t& t1, uint32_t& t2, int& blk) {
     const float4* hn4 = reinterpret_cast<const float4*>(hn_off);
     uint32_t key[64];
 #pragma unroll
@@ -278,7 +277,7 @@ __device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t 
             const int j = j4 * 4 + jj;
             const uint32_t acc = j < 32 ? v0[j & 31] : v1[j & 31];
             const uint32_t tb = MODE == 2 ? acc : __float_as_uint(__uint_as_float(acc) - hh[jj]);
-            key[j] = tb * key_mul + uint32_t(j);
+            key[j] = tb;                                  // positive floats of one binade: integer order == float order
         }
     }
     uint32_t bm[4];
@@ -302,6 +301,7 @@ __device__ __forceinline__ void scan64(const uint32_t (&v0)[32], const uint32_t 
     const uint32_t m01 = max(bm[0], bm[1]), n01 = min(bm[0], bm[1]), m23 = max(bm[2], bm[3]), n23 = min(bm[2], bm[3]);
     t1 = max(m01, m23);
     t2 = __vimax3_u32(min(m01, m23), n01, n23);
+    blk = m23 > m01 ? (bm[3] > bm[2] ? 3 : 2) : (bm[1] > bm[0] ? 1 : 0);     // block of t1 (a tie means t2 == t1: unsafe anyway)
 }
 // Largest value of ch[] outside the chain that holds the overall maximum (= second largest of the 16 chain maxima).
 __device__ __forceinline__ uint32_t chains_runner_up(const uint32_t (&ch)[16]) {
@@ -704,7 +704,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 const uint32_t kbest = max(ca.k1, cc.k1);
                 // every code other than c1 has a key <= kbound
                 const uint32_t kbound = __vimax3_u32(min(ca.k1, cc.k1), ca.k2, cc.k2);
-                const float t_best = key_to_t(kbest, ks.top6), t_bound = key_to_t(kbound, ks.top6);
+                const float t_best = __uint_as_float(kbest), t_bound = __uint_as_float(kbound);
                 const float xn = sqrtf(xx);
                 const float acc_err = 1.2e-7f * float(p.Dp) * xn * e_norm_max;              // FP32 accumulation of D products
                 const float err = sqrtf(rr) * e_norm_max + xn * e_err_max + acc_err + 4.f * ks.ulp;   // FP16 rounding of x and E, roundings of t
@@ -823,7 +823,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         reg_inc<REGS_SCAN>();
         const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 4) >> 2;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
-        const uint32_t key_mul = p.key_mul;
         uint32_t qa = 0, it = 0;
         Ring rc;                                              // hand-off slot of this tile
         Ring rs;                                              // accumulator stage of code tile qa (2 or 3 stages)
@@ -872,15 +871,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
                     t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
 #else
-                    if (p.fold) scan64<2>(v0, v1, nullptr, key_mul, ch, t1, t2);
-                    else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, key_mul, ch, t1, t2);
-                    else scan64<0>(v0, v1, p.hn_off + cbase, key_mul, ch, t1, t2);
+                    int blk;
+                    if (p.fold) scan64<2>(v0, v1, nullptr, ch, t1, t2, blk);
+                    else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, ch, t1, t2, blk);
+                    else scan64<0>(v0, v1, p.hn_off + cbase, ch, t1, t2, blk);
 #endif
                     // fold this half tile into the running pair: r1 = best key, r2 = best key outside the winner's block
                     if (t1 > r1) {
                         r2 = max(r1, t2);
                         r1 = t1;
-                        rc1 = cbase + int(t1 & 63u);
+                        rc1 = cbase + 16 * blk;                                // first column of the winner's block
                     } else {
                         r2 = max(r2, t1);
                     }
@@ -890,7 +890,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const uint32_t cb = rc.i, cph = rc.ph;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
             r2 = max(r2, chains_runner_up(ch));                    // ... and outside the winner's residue chain: the exact runner-up
-            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1; c.pad = 0;
+            int res = 0;                                           // the winner's residue: the chain that holds the maximum
+#pragma unroll
+            for (int j = 1; j < 16; ++j) res = ch[j] == r1 ? j : res;
+            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1 + res; c.pad = 0;
             cand[(cb * 2 + wg) * TM + r] = c;
             mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
             if (warp == 4) VQ_TRACE(9, it);
@@ -986,7 +989,6 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
-    p.key_mul = 64u;
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
 
     if (!p.hn_in_smem) {
