@@ -979,10 +979,13 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     // Three accumulator stages of N = 128 (the tensor core never waits for a scan group to read a stage out) when TMEM
     // can still hold two converted tiles next to them; the constant operand of the folded step then comes from shared memory.
     p.const_smem = 0;
-    // Measured equal to the two-stage N = 256 mode at K = 512, D = 128 (0.0762 vs 0.0768 ms: the CUDA-core work of the scan and
-    // front groups bounds both), so it is opt-in: VQ_K1_STAGES=3.
-    if (const char* e = getenv("VQ_K1_STAGES"))
-        if (atoi(e) == 3 && p.fold && p.resident && 3 * TN + 2 * (w.Dp / 2) <= 512) { p.acc_stages = 3; p.const_smem = 1; }
+    // Measured against the two-stage N = 256 mode (K = 512): 3 % faster at D = 128 on the LJSpeech-like batch (0.0690 vs 0.0713 ms),
+    // equal on equal-length batches, 3.5 % slower at D = 64 -- so it is the default for 64 < D <= 128 only.
+    // VQ_K1_STAGES=2 / 3 overrides (3 only where TMEM allows it).
+    const bool three_fits = p.fold && p.resident && 3 * TN + 2 * (w.Dp / 2) <= 512;
+    bool three = three_fits && w.Dp == 128;
+    if (const char* e = getenv("VQ_K1_STAGES")) three = three_fits && atoi(e) == 3;
+    if (three) { p.acc_stages = 3; p.const_smem = 1; }
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (const char* e = getenv("VQ_K1_PAIR")) p.pair = p.pair && atoi(e) != 0;   // A/B switch for measurements
     if (p.acc_stages != 2) p.pair = 0;

@@ -445,8 +445,9 @@ def test_device_side_restart_rows(vq):
 
 
 def test_three_accumulator_stage_mode(vq, monkeypatch):
-    """VQ_K1_STAGES=3 (three N = 128 accumulator stages, constant operand of the folded k-step read from shared memory
-    through a stride-0 descriptor) must give the same indices as the default two-stage mode and as the oracle."""
+    """The two accumulator layouts of the tcgen05 kernel -- VQ_K1_STAGES=3 (three N = 128 stages, constant operand of the
+    folded k-step read from shared memory through a stride-0 descriptor; default at D = 128) and VQ_K1_STAGES=2 (two stages
+    filled by N = 256 MMAs) -- must give the same indices as each other and as the oracle."""
     gen = torch.Generator().manual_seed(5)
     K, D = 512, 128
     code = torch.randn(K, D, generator=gen)
@@ -457,6 +458,7 @@ def test_three_accumulator_stage_mode(vq, monkeypatch):
     rows, _, _ = O.flatten_nct(x, mask)
     o_l = O.assign(rows, code)[0]
     xd, kd = x.to(DEV), code.to(DEV)
+    monkeypatch.setenv("VQ_K1_STAGES", "2")
     base = vq.assign(xd, kd, algo="tc")[0].cpu()
     monkeypatch.setenv("VQ_K1_STAGES", "3")
     three = vq.assign(xd, kd, algo="tc")[0].cpu()
