@@ -74,6 +74,7 @@ struct Params {
     int pair;                // even number of code tiles: MMAs are issued with N = 256 over two adjacent B tiles
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
+    uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
 
@@ -138,6 +139,14 @@ struct TileWalk {
     __device__ __forceinline__ TileWalk(int tile, int per) : n(tile / per), t(tile % per) {}
     __device__ __forceinline__ void advance(int step, int per) { t += step; while (t >= per) { t -= per; ++n; } }
 };
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    do {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (++spins > SPIN_LIMIT) __trap();
+    } while (!mbar_try_wait(bar, parity));
+}
 // One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
 // asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
 // compiler wrap every tcgen05.mma / TMA in an ELECT + R2UR.BROADCAST loop, ~190 cycles per instruction).
@@ -838,8 +847,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 // other group's arithmetic on the same scheduler instead of both stalling together.
                 if ((qa & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
-                // suspended wait: as fast as a spinning test_wait (measured) without burning a third of the issue slots
-                mbar_wait<0>(smem_u32(&ctl->acc_full[s]), sph);
+                // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
+                // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
+                mbar_wait_backoff(smem_u32(&ctl->acc_full[s]), sph, p.scan_sleep_ns);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4) VQ_TRACE_NT(12, it, nt);
@@ -992,6 +1002,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
+    p.scan_sleep_ns = 64;                                        // (0 .. 250 ns measured within 1 % of each other)
+    if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) p.scan_sleep_ns = uint32_t(atoi(e));
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
 
     if (!p.hn_in_smem) {
