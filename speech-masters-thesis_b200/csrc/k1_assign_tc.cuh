@@ -1,25 +1,28 @@
 // K1 (fast path): the distance contraction x.E^T on the 5th-generation tensor cores (tcgen05, sm_100a).
 // Replaces bottleneck.py:92-100 (NCT flatten, fused away), :129-134 (distance + argmin) and the numerator of :140.
 //
-// One persistent CTA per SM, 16 warps, warp-specialised:
+// One persistent CTA per SM, 16 warps, warp-specialised; after the prologue the register file is re-split with setmaxnreg
+// (issuers 40, front group 120, scan groups 176 registers per thread):
 //   warp 12       TMA producer for x: FP32 [32 depth x 128 frames] boxes straight out of the NCT tensor
 //   warp 13       MMA issuer (one lane): tcgen05.mma kind::f16, A (frames x depth, FP16) from TMEM, B (codes x depth,
-//                 FP16, 128B-swizzled K-major) from shared memory, FP32 accumulators in TMEM (2 stages x 128 columns)
+//                 FP16, 128B-swizzled K-major) from shared memory, FP32 accumulators in TMEM: two 128-column stages filled
+//                 by N = 256 instructions, or (64 < D <= 128) three stages filled by N = 128 instructions; in the resident
+//                 steady state a tile's MMAs are straight-line code
 //   warp 14       TMA producer for the FP16 codebook image (resident in shared memory when it fits, else a ring)
 //   warp 15       TMEM allocator
-//   warps 0-3     front/back group: (front) FP32 smem tile -> FP16 pairs -> tcgen05.st into one of up to four TMEM
-//                 A buffers (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and
+//   warps 0-3     front/back group: (front) FP32 smem tile -> FP16 pairs -> tcgen05.st into a TMEM A buffer
+//                 (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and
 //                 the FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) a few tiles later: merge the two
 //                 scan groups' candidates, run the provable safety test, write idx (optionally re-score in FP32)
-//   warps 4-11    scan groups: tcgen05.ld the accumulators (thread == frame; the two groups take alternate 128-code
-//                 tiles) and keep a branch-free running (best, runner-up) over integer keys
+//   warps 4-11    scan groups (thread == frame; the two groups take alternate 128-code tiles): tcgen05.ld a WHOLE
+//                 accumulator stage into registers, hand the stage back to the tensor core, then scan it
 //
-// Keys.  The score of code c for frame r is s = x.e_c - ||e_c||^2/2 (argmax s == argmin distance).  The scan computes
-// t = acc - (||e_c||^2/2 - B) with B = 1.5 * 2^E, E chosen per launch so that every in-range score lands in
-// [2^E, 2^(E+1)): all t share one exponent, so their bit patterns order like the scores and
-// key = (bits(t) << 6) | column is ONE integer multiply-add on the FMA pipe (no mask, no precision loss); best and
-// runner-up then cost 5 integer min/max (2.5 per code) on the ALU pipe.  Frames whose norm would leave the range are
-// sent to the exact fallback.
+// Keys.  The score of code c for frame r is s = x.e_c - ||e_c||^2/2 (argmax s == argmin distance).  The accumulator holds
+// t = acc - (||e_c||^2/2 - B) (the offset rides in the MMA as one extra k-step when the codebook is resident), with
+// B = 1.5 * 2^E, E chosen per launch so that every in-range score lands in [2^E, 2^(E+1)): all t share one exponent, so
+// their raw bit patterns, compared as unsigned integers, order like the scores -- no per-code arithmetic at all.  Best and
+// exact runner-up cost ~1.2 three-input integer max per code through two families of running maxima (see scan64), and
+// the winner's column is read off the two families.  Frames whose norm would leave the range go to the exact fallback.
 //
 // Exactness: FP16 operands only SHORTLIST.  A frame keeps the shortlisted code iff the best key beats the runner-up by
 // more than twice a rigorous bound on the FP16 error,
