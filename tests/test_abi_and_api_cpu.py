@@ -98,6 +98,14 @@ def test_cpu_tensors_fail_loudly():
         blk(torch.zeros(1, 4, 3), torch.ones(1, 1, 3), update_k=False)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk.decode(torch.zeros(1, 3, dtype=torch.int64))
+    from importlib import import_module
+    q = import_module(vqb200.__name__ + ".quantizer")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q.restart_rows_device(torch.zeros(1, 4, 3), None, 8, torch.zeros(1, dtype=torch.int64))
+    fast = vqb200.BottleneckBlock(8, 4, 0.99, 1.0, rng_parity=False)      # the device-RNG mode has no CPU path either
+    fast.train()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fast(torch.zeros(1, 4, 3), torch.ones(1, 1, 3), update_k=True)
 
 
 def test_product_never_imports_oracle():
