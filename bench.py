@@ -40,13 +40,15 @@ def env_int(name, default):
         return default
 
 
-def make_batch(n_utt, seed):
+def make_batch(n_utt, seed, clustered=True):
+    """SURVEY.md 8d inputs: (C) clustered latents E[j] + 0.5 N(0,1), Zipf-skewed j (speech-like) or (G) i.i.d. N(0,1)
+    (the adversarial case for near-ties)."""
     import torch
     from oracle import vq_oracle as O          # synthetic-input recipe only (SURVEY.md 8d); not on the timed path
     gen = torch.Generator().manual_seed(seed)
     code = torch.randn(K_BINS, EMB, generator=gen)
     lengths = O.ljspeech_like_lengths(n_utt, gen)
-    x, mask = O.synthetic_batch(lengths, EMB, gen, codebook=code)
+    x, mask = O.synthetic_batch(lengths, EMB, gen, codebook=code if clustered else None)
     return x, mask, lengths, code
 
 
@@ -95,26 +97,58 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(budget_s, batch_utt=8, seed=100):
-    """Frames/s of the CPU port of the reference encode path, as shipped (NT x NT `fit` temporary included),
-    and of the same path without that temporary.  Bounded to ~budget_s seconds."""
+def reference_block(code):
+    """The CPU arm's quantiser: the UNMODIFIED reference ``BottleneckBlock`` when baseline/_ref is staged
+    (kind "reference"), else the oracle port (kind "port").  Returns (kind, encode(x, mask), forward_train(x, mask))."""
+    import torch
+    from oracle import stage_ref, vq_oracle as O
+    if stage_ref.activate():
+        from models.vqvae.bottleneck import BottleneckBlock
+        blk = BottleneckBlock(K_BINS, EMB, 0.99, 1.0)
+        blk.k = code.clone()
+        blk.k_sum, blk.k_elem, blk.init = code.clone() * 4, torch.full((K_BINS,), 4.0), True
+        blk.train()
+
+        def fwd(x, mask):
+            with torch.no_grad():
+                return blk(x, mask, update_k=True)
+
+        return "reference", (lambda x, mask: blk.encode(x, mask)), fwd
+    st = O.CodebookState(K_BINS, EMB, 0.99, 1.0, code.clone(), code.clone() * 4, torch.full((K_BINS,), 4.0), True)
+    return ("port", (lambda x, mask: O.encode(st, x, mask, faithful_fit=True)),
+            (lambda x, mask: O.forward(st, x, mask, update_k=True, faithful_fit=True)))
+
+
+def _rate(fn, frames, budget_s, max_reps=50):
+    fn()                                                        # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        fn()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= max_reps:
+            break
+    return frames * n / (time.perf_counter() - t0)
+
+
+def cpu_reference_rates(budget_s):
+    """Frames/s of the reference's CPU path on this box's host cores, bounded to ~budget_s seconds:
+    BASELINE.json configs[0] (forward + EMA update, batch 16), the generate-script encode (batch 8, script default), and
+    the port's encode without the NT x NT `fit` temporary (so that artefact is visible separately)."""
     import torch
     from oracle import vq_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    x, mask, lengths, code = make_batch(batch_utt, seed)
+    x8, m8, l8, code = make_batch(8, 100)
+    x16, m16, l16, _ = make_batch(16, 101)
+    kind, enc, fwd = reference_block(code)
     st = O.CodebookState(K_BINS, EMB, k=code, init=True)
-    valid = int(lengths.sum())
-    out = {}
-    for name, faithful in (("as_shipped", True), ("without_nxn_temp", False)):
-        O.encode(st, x, mask, faithful_fit=faithful)            # warm-up
-        t0, n = time.perf_counter(), 0
-        while True:
-            O.encode(st, x, mask, faithful_fit=faithful)
-            n += 1
-            if time.perf_counter() - t0 > budget_s / 2 or n >= 50:
-                break
-        out[name] = valid * n / (time.perf_counter() - t0)
-    return out, torch.get_num_threads(), f"{batch_utt} utterances/batch ({valid} valid frames, {x.shape[0] * x.shape[2]} rows)"
+    out = {
+        "forward_train_b16": _rate(lambda: fwd(x16, m16), int(l16.sum()), budget_s / 3),
+        "encode_b8": _rate(lambda: enc(x8, m8), int(l8.sum()), budget_s / 3),
+        "encode_b8_without_nxn_temp": _rate(lambda: O.encode(st, x8, m8, faithful_fit=False), int(l8.sum()), budget_s / 3),
+    }
+    sample = (f"encode: 8 utterances/batch ({int(l8.sum())} valid frames, {x8.shape[0] * x8.shape[2]} rows); "
+              f"forward+EMA (configs[0]): 16 utterances ({int(l16.sum())} valid frames, {x16.shape[0] * x16.shape[2]} rows)")
+    return out, kind, torch.get_num_threads(), sample
 
 
 def run_reference(args):
@@ -122,20 +156,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     import torch
-    from oracle import vq_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    st = None
     batches = []
     per_step_utts = 32                      # bounded sample of the 256-utterance step, in script-default batches of 8
+    code = None
     for b in range(per_step_utts // 8):
-        x, mask, lengths, code = make_batch(8, 1000 + b)
+        x, mask, lengths, c = make_batch(8, 1000 + b)
+        code = c if code is None else code
         batches.append((x, mask, int(lengths.sum())))
-        st = st or O.CodebookState(K_BINS, EMB, k=code, init=True)
+    kind, enc, _ = reference_block(code)
     frames = sum(b[2] for b in batches)
 
     def step():
         for x, mask, _ in batches:
-            O.encode(st, x, mask, faithful_fit=True)
+            enc(x, mask)
 
     for _ in range(min(args.warmup, 2)):
         step()
@@ -148,14 +182,16 @@ def run_reference(args):
             break
     dt = time.perf_counter() - t0
     value = frames * done / dt
+    what = ("the unmodified reference BottleneckBlock.encode (baseline/_ref)" if kind == "reference"
+            else "CPU port of the reference (oracle/vq_oracle.py)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "steps_timed": done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ljspeech-like corpus encode (BottleneckBlock.encode), K=512 D=128, CPU port of the reference",
+        "config": {"workload": "ljspeech-like corpus encode (BottleneckBlock.encode), K=512 D=128, " + what,
                    "k_bins": K_BINS, "emb_width": EMB, "utterances_per_step": per_step_utts, "batch_size": 8,
                    "frames_per_step": frames},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": f"{per_step_utts} utterances per step in batches of 8 (script default), as shipped "
                                    "(NT x NT fit temporary included)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,61 +218,84 @@ def run_b200(args):
     import vqb200
     lib = vqb200._lib.load()
     from oracle import vq_oracle as O
-
-    # ---- this rank's shard of the corpus: one 256-utterance batch per step (weak scaling)
-    x, mask, lengths, code = make_batch(UTT_PER_STEP, seed=rank)
-    n, d, t = x.shape
-    valid_frames, rows = int(lengths.sum()), n * t
-    xd, kd = x.to(dev), code.to(dev)
-    idx = torch.empty(n, t, dtype=torch.int64, device=dev)
-    ws = torch.empty(int(lib.vq_workspace_bytes(n, t, K_BINS, EMB)), dtype=torch.uint8, device=dev)
-    scalars = torch.zeros(16, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-
-    prepared = [0]
-
-    def step():
-        # frozen codebook, many batches (generate_vq_dataset.py): the codebook operands are prepared by the first call only
-        rc = lib.vq_assign(xd.data_ptr(), n, d, t, kd.data_ptr(), K_BINS, idx.data_ptr(), None, None,
-                           ws.data_ptr(), ws.numel(), prepared[0], stream)
-        prepared[0] = 256
-        if rc:
-            raise RuntimeError(lib.vq_last_error().decode())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
+    # ---- this rank's shard of the corpus: one 256-utterance batch per step (weak scaling); (C) clustered latents are the
+    # headline, (G) i.i.d. Gaussian latents the adversarial case (2 % of the frames take the exact re-scan)
+    class Job:
+        def __init__(self, clustered):
+            self.x, self.mask, self.lengths, self.code = make_batch(UTT_PER_STEP, seed=rank, clustered=clustered)
+            self.n, self.d, self.t = self.x.shape
+            self.valid, self.rows = int(self.lengths.sum()), self.n * self.t
+            self.xd, self.kd = self.x.to(dev), self.code.to(dev)
+            self.idx = torch.empty(self.n, self.t, dtype=torch.int64, device=dev)
+            self.ws = torch.empty(int(lib.vq_workspace_bytes(self.n, self.t, K_BINS, EMB)), dtype=torch.uint8, device=dev)
+            self.prepared = 0
+
+        def step(self):
+            # frozen codebook, many batches (generate_vq_dataset.py): the codebook operands are prepared by the first call only
+            rc = lib.vq_assign(self.xd.data_ptr(), self.n, self.d, self.t, self.kd.data_ptr(), K_BINS, self.idx.data_ptr(), None,
+                               None, self.ws.data_ptr(), self.ws.numel(), self.prepared, stream)
+            self.prepared = 256
+            if rc:
+                raise RuntimeError(lib.vq_last_error().decode())
+
+        def timed(self, steps, warmup):
+            for _ in range(max(3, warmup)):
+                self.step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.step()
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
+
+        def profile(self, steps):
+            # per-kernel times from a second, short pass with the library's event profiler on (its event records between the
+            # kernels would otherwise sit inside the timed region and serialise the dependent launch of the re-scan)
+            lib.vq_profile_enable(1)
+            for _ in range(min(steps, 32)):
+                self.step()
+            torch.cuda.synchronize()
+            prof = (ctypes.c_float * 4)()
+            ok = lib.vq_profile_read(prof) == 0
+            lib.vq_profile_enable(0)
+            return [float(v) for v in prof] if ok else None
+
+        def unsafe_rows(self):
+            scalars = torch.zeros(16, dtype=torch.float64, device=dev)
+            lib.vq_assign(self.xd.data_ptr(), self.n, self.d, self.t, self.kd.data_ptr(), K_BINS, self.idx.data_ptr(), None,
+                          scalars.data_ptr(), self.ws.data_ptr(), self.ws.numel(), 0, stream)
+            self.prepared = 0
+            return float(scalars[vqb200._lib.S_UNSAFE_ROWS].item())
+
+    job = Job(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # per-kernel times of the same step from a second, short pass with the library's event profiler on (its event records
-    # between the kernels would otherwise sit inside the timed region and serialise the dependent launch of the re-scan)
-    lib.vq_profile_enable(1)
-    for _ in range(min(args.steps, 32)):
-        step()
-    torch.cuda.synchronize()
-    prof = (ctypes.c_float * 4)()
-    have_prof = lib.vq_profile_read(prof) == 0
-    lib.vq_profile_enable(0)
-    # one untimed call with the scalar block attached: how many frames took the exact fallback
-    lib.vq_assign(xd.data_ptr(), n, d, t, kd.data_ptr(), K_BINS, idx.data_ptr(), None, scalars.data_ptr(),
-                  ws.data_ptr(), ws.numel(), 0, stream)
-    unsafe = float(scalars[vqb200._lib.S_UNSAFE_ROWS].item())
+    ms = job.timed(args.steps, args.warmup)
+    prof = job.profile(args.steps)
+    unsafe = job.unsafe_rows()
     if args.profile_only:
-        print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "k1_ms": float(prof[1])}))
+        print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "k1_ms": prof[1] if prof else None}))
         return 0
+    # sustained: the same step back to back for >= 1 s (the headline region is only steps x 0.07 ms)
+    sus_steps = max(args.steps, int(1.2e3 / max(ms / args.steps, 1e-3)))
+    sus_ms = job.timed(sus_steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    gjob = Job(False)
+    g_ms = gjob.timed(args.steps, args.warmup)
+    g_prof = gjob.profile(args.steps)
+    g_unsafe = gjob.unsafe_rows()
+    n, d, t, rows, valid_frames = job.n, job.d, job.t, job.rows, job.valid
+    x, mask, code, xd, kd, idx = job.x, job.mask, job.code, job.xd, job.kd, job.idx
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
     ctx = lib.vq_host_ctx_create(local, rows, K_BINS, EMB)
@@ -254,11 +313,10 @@ def run_b200(args):
             raise RuntimeError(lib.vq_last_error().decode())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     idx_host = torch.frombuffer((ctypes.c_int64 * rows).from_address(hidx), dtype=torch.int64).clone()
     lib.vq_host_ctx_destroy(ctx)
 
-    # whole training-mode forward of the module on every rank (K1 + K2 + K3a + ONE all-reduce + K3b + restart-row glue)
+    # whole training-mode forward of the module on every rank (K1 + K3a + {ONE all-reduce || K2} + K3b + restart-row glue)
     def timed_all(fn, reps=5):
         for _ in range(2):
             fn()
@@ -281,6 +339,15 @@ def run_b200(args):
     fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
     blk.rng_parity = False                   # restart rows drawn on the device: no host sync, no CPU randperm
     fwd_fast_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
+    # replicas must still be bit-identical after all those all-reduced updates (bottleneck.py:72-75)
+    replicas_identical = None
+    if world > 1:
+        digest = torch.stack([blk.k.double().sum(), blk.k_sum.double().sum(), blk.k_elem.double().sum(),
+                              (blk.k.double() ** 2).sum()])
+        all_digests = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(all_digests, digest)
+        replicas_identical = all(torch.equal(all_digests[0], g) for g in all_digests)
+        assert replicas_identical, "codebook replicas diverged across ranks"
     # the same forward replayed from a CUDA graph (no host launch cost; static input addresses, as any graphed module)
     fwd_graph_ms = None
     try:
@@ -298,13 +365,13 @@ def run_b200(args):
             g_out = blk(xd, md_all, update_k=True)
         fwd_graph_ms = timed_all(graph.replay)
         del graph, g_out
-    except Exception as exc:                                  # noqa: BLE001  (reported, never fatal for the bench line)
+    except Exception:                                          # noqa: BLE001  (reported as null, never fatal for the bench line)
         fwd_graph_ms = None
-        graph_error = repr(exc)[:200]
     del blk
 
-    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms, fwd_graph_ms if fwd_graph_ms else 0.0], dtype=torch.float64, device=dev)
-    frames = torch.tensor([float(valid_frames), float(rows)], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms, fwd_graph_ms if fwd_graph_ms else 0.0, sus_ms, g_ms],
+                         dtype=torch.float64, device=dev)
+    frames = torch.tensor([float(valid_frames), float(rows), float(gjob.valid), float(gjob.rows)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, dist.ReduceOp.MAX)
         dist.all_reduce(frames, dist.ReduceOp.SUM)
@@ -312,17 +379,23 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms = (float(times[i]) for i in range(5))
-    tot_valid, tot_rows = float(frames[0]), float(frames[1])
+    ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms, sus_ms, g_ms = (float(times[i]) for i in range(7))
+    tot_valid, tot_rows, g_tot_valid = float(frames[0]), float(frames[1]), float(frames[2])
     value = tot_valid * args.steps / (ms * 1e-3)
     e2e_value = tot_valid * args.steps / (e2e_ms * 1e-3)
 
-    # ---- parity spot check against the oracle (outside every timed region)
-    sample = 4
-    rows_cpu, _, _ = O.flatten_nct(x[:sample], mask[:sample])
-    o_l, _, _ = O.assign(rows_cpu, code)
-    audit = O.audit_indices(rows_cpu, code, o_l, idx[:sample].cpu().reshape(-1))
-    audit_host = O.audit_indices(rows_cpu, code, o_l, idx_host.view(n, t)[:sample].reshape(-1))
+    # ---- parity audit against the oracle, EVERY row of both batches (outside every timed region): the oracle's
+    # quantize(x, mask=None) over 8k-row chunks; each disagreement is classified in fp64 (near-tie or error)
+    def full_audit(j, got):
+        rows_cpu = j.x.permute(0, 2, 1).reshape(-1, j.d)
+        o_l, _ = O.assign_chunked(rows_cpu, j.code)
+        return O.audit_indices(rows_cpu, j.code, o_l, got.cpu().reshape(-1))
+
+    audit = full_audit(job, idx)
+    audit_host = full_audit(job, idx_host)
+    audit_gauss = full_audit(gjob, gjob.idx)
+    assert audit["rows"] == rows and audit["errors"] == 0 and audit_host["errors"] == 0 and audit_gauss["errors"] == 0, \
+        (audit, audit_host, audit_gauss)
 
     # ---- roofline of the dominant kernel (K1): algorithmic flops = 2 * rows * K * D per launch
     peaks = {}
@@ -331,24 +404,45 @@ def run_b200(args):
     except (OSError, ValueError):
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sus = float(peaks.get("bf16_tflops_sustained", peak_tf))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 TFLOP/s"
-    k1_ms = float(prof[1]) if have_prof and prof[1] > 0 else ms / args.steps
+    have_prof = prof is not None and prof[1] > 0
+    k1_ms = prof[1] if have_prof else ms / args.steps
     flops = 2.0 * rows * K_BINS * EMB
     achieved = flops / (k1_ms * 1e-3) / 1e12
     hbm_bytes = rows * (4 * EMB + 8) + 4 * K_BINS * EMB
     traffic = None
-    try:        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))["traffic_bytes_per_launch"]
-    except (OSError, ValueError, KeyError):
-        pass
+    for name in ("r02_k1_traffic.json", "r01_k1_traffic.json"):
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["traffic_bytes_per_launch"]
+            break
+        except (OSError, ValueError, KeyError):
+            pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": traffic, "algorithmic_flop_per_launch": flops, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src, "kernel": "K1 distance+argmin (vq_assign main kernel)",
-                "kernel_ms": k1_ms, "kernel_ms_source": "library CUDA events around the kernel" if have_prof and prof[1] > 0
+                "traffic": traffic, "algorithmic_flop_per_launch": flops, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src,
+                "kernel": "K1 distance+argmin (vq_assign main kernel), clustered latents",
+                "kernel_ms": k1_ms, "kernel_ms_source": "library CUDA events around the kernel" if have_prof
                 else "whole vq_assign step (prep + main + fallback kernels)",
-                "hbm_secondary": {"achieved_GBps": hbm_bytes / (k1_ms * 1e-3) / 1e9, "peak_GBps": float(peaks.get("hbm_gbs", 6650.0))}}
+                "hbm_secondary": {"achieved_GBps": hbm_bytes / (k1_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak}}
     if have_prof:
-        roofline["step_breakdown_ms"] = {"codebook_prepare": float(prof[0]), "assign_main": float(prof[1]),
-                                         "exact_fallback": float(prof[2])}
+        roofline["step_breakdown_ms"] = {"codebook_prepare": prof[0], "assign_main": prof[1], "exact_fallback": prof[2]}
+    sus_step_ms = sus_ms / sus_steps
+    roofline["sustained"] = {"steps": sus_steps, "seconds": sus_ms * 1e-3, "ms_per_step": sus_step_ms,
+                             "tflops_whole_step": flops / (sus_step_ms * 1e-3) / 1e12,
+                             "frac_of_burst_peak": flops / (sus_step_ms * 1e-3) / 1e12 / peak_tf,
+                             "frac_of_sustained_peak": flops / (sus_step_ms * 1e-3) / 1e12 / peak_sus,
+                             "sm_mhz_median": clocks.get("sm_mhz") if clocks else None}
+    # the adversarial distribution as a first-class number: whole step = main kernel + exact re-scan of the unsafe frames
+    g_flops = 2.0 * gjob.rows * K_BINS * EMB
+    g_step_ms = g_ms / args.steps
+    gaussian = {"value": g_tot_valid * args.steps / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_step_ms,
+                "unsafe_rows_per_step": g_unsafe, "unsafe_frac": g_unsafe / gjob.rows,
+                "roofline_whole_step": {"achieved": g_flops / (g_step_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                        "frac": g_flops / (g_step_ms * 1e-3) / 1e12 / peak_tf},
+                "index_match": audit_gauss}
+    if g_prof:
+        gaussian["step_breakdown_ms"] = {"codebook_prepare": g_prof[0], "assign_main": g_prof[1], "exact_fallback": g_prof[2]}
 
     # ---- the other kernels of the training path at the same batch: each timed alone, CUDA events around 10 back-to-back
     # calls (the 228 MB input exceeds L2, so every call streams from HBM), best of 3
@@ -368,7 +462,7 @@ def run_b200(args):
         return best
 
     md = mask.to(dev)
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    scalars = torch.zeros(16, dtype=torch.float64, device=dev)
     x_q = torch.empty_like(xd)
     res = torch.zeros(8, device=dev)
     stats = torch.zeros(K_BINS * EMB + K_BINS, device=dev)
@@ -384,28 +478,31 @@ def run_b200(args):
     k3_fin = timed(lambda: lib.vq_ema_finalize(stats.data_ptr(), kd.data_ptr(), kd.data_ptr(), k_new.data_ptr(), k_sum.data_ptr(),
                                                k_elem.data_ptr(), K_BINS, EMB, 0.99, 1.0, 0.0, scalars.data_ptr(), res.data_ptr(), None, stream))
 
-    def gbps(nbytes, ms_):
-        return nbytes / (ms_ * 1e-3) / 1e9
+    def hbm_line(name, ms_, nbytes):
+        gbps = nbytes / (ms_ * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "ms": ms_, "algorithmic_bytes": nbytes, "achieved": gbps, "peak": hbm_peak,
+                "unit": "GB/s", "frac": gbps / hbm_peak}
 
-    other = {
-        "K2_gather_st_fwd": {"ms": k2_fwd, "algorithmic_bytes": rows * (8 * EMB + 12), "GBps": gbps(rows * (8 * EMB + 12), k2_fwd)},
-        "K2_gather_st_bwd": {"ms": k2_bwd, "algorithmic_bytes": rows * (12 * EMB + 12), "GBps": gbps(rows * (12 * EMB + 12), k2_bwd)},
-        "K2_decode": {"ms": k2_dec, "algorithmic_bytes": rows * (4 * EMB + 8), "GBps": gbps(rows * (4 * EMB + 8), k2_dec)},
-        "K3_ema_accumulate": {"ms": k3_acc, "algorithmic_bytes": valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1),
-                              "GBps": gbps(valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1), k3_acc)},
-        "K3_ema_finalize": {"ms": k3_fin, "algorithmic_bytes": 4 * K_BINS * (6 * EMB + 3), "GBps": gbps(4 * K_BINS * (6 * EMB + 3), k3_fin)},
+    rooflines = [
+        hbm_line("K2 vq_gather_st_fwd", k2_fwd, rows * (8 * EMB + 12)),
+        hbm_line("K2 vq_gather_st_bwd", k2_bwd, rows * (12 * EMB + 12)),
+        hbm_line("K2 vq_decode", k2_dec, rows * (4 * EMB + 8)),
+        hbm_line("K3a vq_ema_accumulate", k3_acc, valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1)),
+        hbm_line("K3b vq_ema_finalize", k3_fin, 4 * K_BINS * (6 * EMB + 3)),
+    ]
+    training = {
+        "module_forward_train": {"ms": fwd_ms, "valid_frames_per_s": tot_valid / (fwd_ms * 1e-3),
+                                 "note": "whole nn.Module training forward per rank (K1+K3a+{all-reduce||K2}+K3b+restart-row glue, "
+                                         "rng_parity=True: CPU randperm replay), max over ranks"},
+        "module_forward_train_device_rng": {"ms": fwd_fast_ms, "valid_frames_per_s": tot_valid / (fwd_fast_ms * 1e-3),
+                                            "note": "same with rng_parity=False (restart rows drawn on the device, no host sync)"},
+        "replicas_bit_identical_after_allreduce": replicas_identical,
     }
-    for v in other.values():
-        v["frac_of_hbm_peak"] = v["GBps"] / hbm_peak
-    other["module_forward_train"] = {"ms": fwd_ms, "valid_frames_per_s": tot_valid / (fwd_ms * 1e-3),
-                                     "note": "whole nn.Module training forward per rank (K1+K2+K3a+all-reduce+K3b+restart-row glue), max over ranks"}
-    other["module_forward_train_device_rng"] = {"ms": fwd_fast_ms, "valid_frames_per_s": tot_valid / (fwd_fast_ms * 1e-3),
-                                                "note": "same with rng_parity=False (restart rows drawn on the device, no host sync)"}
     if fwd_graph_ms:
-        other["module_forward_train_cuda_graph"] = {"ms": fwd_graph_ms, "valid_frames_per_s": tot_valid / (fwd_graph_ms * 1e-3),
-                                                    "note": "rng_parity=False forward captured once with torch.cuda.graph and replayed"}
+        training["module_forward_train_cuda_graph"] = {"ms": fwd_graph_ms, "valid_frames_per_s": tot_valid / (fwd_graph_ms * 1e-3),
+                                                       "note": "rng_parity=False forward captured once with torch.cuda.graph and replayed"}
 
-    cpu, cores, sample_desc = cpu_reference_rate(budget_s=16.0)
+    cpu, cpu_kind, cores, sample_desc = cpu_reference_rates(budget_s=18.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -413,6 +510,7 @@ def run_b200(args):
         "config": {"workload": "ljspeech-like corpus encode (BottleneckBlock.encode / generate_vq_dataset.py:69), K=512 D=128",
                    "k_bins": K_BINS, "emb_width": EMB, "utterances_per_step_per_gpu": UTT_PER_STEP,
                    "rows_per_step_per_gpu": rows, "valid_frames_per_step_per_gpu": valid_frames, "layout": "NCT fp32",
+                   "latents": "clustered (speech-like); the i.i.d. Gaussian batch is reported under `gaussian`",
                    "l2": "inputs (228 MB per step) exceed the 126 MB L2; no flush needed", "parallelism": f"frames sharded x{world}, codebook replicated"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * d * 4, "d2h_bytes_per_step": rows * 8,
                 "ms_per_step": e2e_ms / args.steps, "api": "vq_encode_host (pinned host buffers, chunked double-buffered copies)",
@@ -420,10 +518,13 @@ def run_b200(args):
         "gpu_launches": args.steps * 2,   # assign_tc + exact-fallback kernel per step (the codebook is prepared once, before the loop)
         "clocks": clocks,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu["as_shipped"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,
-                         "without_nxn_temp": cpu["without_nxn_temp"]},
-        "index_match": {"device_path": audit, "host_path": audit_host},
-        "training_path_kernels": other,
+        "rooflines": rooflines,
+        "gaussian": gaussian,
+        "cpu_baseline": {"value": cpu["encode_b8"], "unit": UNIT, "cores": cores, "kind": cpu_kind, "sample": sample_desc,
+                         "configs0_forward_train_b16": cpu["forward_train_b16"],
+                         "encode_without_nxn_temp": cpu["encode_b8_without_nxn_temp"]},
+        "index_match": {"device_path": audit, "host_path": audit_host, "gaussian": audit_gauss},
+        "training_path": training,
         "unsafe_rows_per_step": unsafe,
     }
     print(json.dumps(line))

@@ -2,7 +2,7 @@
  *
  * Drop-in boundary for ONE path of vliu15/speech-masters-thesis: models/vqvae/bottleneck.py.
  * The reference has no FFI layer (it is pure PyTorch); every entry point below cites the reference
- * lines whose work it replaces.  The Python module speech-masters-thesis_b200/bottleneck.py binds these
+ * lines whose work it replaces.  The Python module speech-masters-thesis_b200/quantizer.py (via _lib.py) binds these
  * with ctypes (tensor.data_ptr(), torch.cuda.current_stream().cuda_stream) and keeps the reference's
  * nn.Module surface; INTEGRATION.md shows the binding a maintainer would add.
  *
@@ -53,6 +53,7 @@ enum {
     VQ_S_USAGE       = 7,
     VQ_S_DK_SQ       = 8,
     VQ_S_TICKET      = 9,   /* last-block tickets */
+    VQ_S_ELEM_TOTAL  = 10,  /* sum of the updated cluster sizes k_elem (the n of the optional Laplace smoothing) */
     VQ_NUM_SCALARS   = 16
 };
 
@@ -72,15 +73,17 @@ const char* vq_last_error(void);
 /* 1 when the current device can run the tcgen05 kernels (compute capability 10.x), else 0. */
 int         vq_device_supported(void);
 
-/* Bytes of scratch vq_assign needs for this shape (BF16 codebook image, norms, fallback worklist). */
+/* Bytes of scratch vq_assign needs for this shape (FP16 codebook image, norms, fallback worklist). */
 size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_width);
 
 /* K1 -- replaces BottleneckBlock.preprocess + quantize (bottleneck.py:92-100,126-141) and, for the
  * generate script, BottleneckBlock.encode (bottleneck.py:147-158; caller scripts/generate_vq_dataset.py:69).
  *   x [N,D,T] fp32, k [K,D] fp32  ->  idx [N*T] int64 (argmin, lowest index on ties),
  *   min_d [N*T] fp32 or NULL, scalars[VQ_S_SUM_MIN_D] += sum(min_d) (scalars may be NULL).
- * The distance is ||x||^2 - 2 x.e + ||e||^2 evaluated in FP32 for the winner exactly as the reference
- * expression does; the tcgen05 path only uses BF16 to shortlist candidates. */
+ * The tcgen05 path uses FP16 operands only to SHORTLIST (best, runner-up) per frame; a frame keeps the shortlisted code
+ * only when its margin exceeds a rigorous bound on the FP16 error, every other frame is re-scanned by the exact FP32
+ * kernel (lowest index on ties, like torch.min).  min_d / sum(min_d), when requested, are ||x||^2 - 2 x.e + ||e||^2
+ * evaluated in FP32 for the winner exactly as the reference expression does. */
 int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames,
               const float* k, int k_bins,
               int64_t* idx, float* min_d, double* scalars,
@@ -140,7 +143,8 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask,
  * (bottleneck.py:69-70,73).  results[VQ_R_ENTROPY..VQ_R_USED_CURR] and *used_curr (int64, may be NULL)
  * are written by the last block.  mu and threshold are the Python floats of the reference (the kernel
  * rounds mu and (1 - mu) to FP32 separately, as `mu * t + (1. - mu) * s` does).  laplace_eps = 0 reproduces the reference (it has no smoothing);
- * a positive value applies k_elem <- (k_elem + eps) / (n + K eps) * n before the division. */
+ * a positive value divides k_sum by (k_elem + eps) / (n + K eps) * n with n = sum_c k_elem[c] (the updated cluster sizes);
+ * k_elem itself is stored unsmoothed. */
 int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old, float* k, float* k_sum, float* k_elem,
                     int k_bins, int emb_width, double mu, double threshold, double laplace_eps,
                     double* scalars, float* results, int64_t* used_curr, void* stream);

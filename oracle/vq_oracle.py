@@ -119,6 +119,18 @@ def assign(rows: torch.Tensor, k: torch.Tensor, mcol: Optional[torch.Tensor] = N
     return x_l, fit, min_d
 
 
+def assign_chunked(rows: torch.Tensor, k: torch.Tensor, chunk: int = 8192) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``quantize(x, mask=None)`` (bottleneck.py:128-134) over row chunks, so that shapes whose [NT, K] distance matrix
+    (or the NT x NT ``fit`` temporary) would not fit host memory can still be audited row for row.  Each row's
+    distances are the same fp32 expression as in ``assign``.  Returns (x_l int64 [NT], min_d [NT])."""
+    idx = torch.empty(rows.shape[0], dtype=torch.int64)
+    min_d = torch.empty(rows.shape[0], dtype=rows.dtype)
+    for a in range(0, rows.shape[0], chunk):
+        m, i = torch.min(distances(rows[a:a + chunk], k), dim=-1)
+        idx[a:a + chunk], min_d[a:a + chunk] = i, m
+    return idx, min_d
+
+
 def gather(x_l: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
     """bottleneck.py:143-145 ``dequantize``."""
     return F.embedding(x_l, k)

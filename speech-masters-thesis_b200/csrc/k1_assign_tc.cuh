@@ -950,6 +950,77 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 }  // namespace tc
 
+// Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
+// VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
+struct TcEnv {
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1;
+    TcEnv() {
+        if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
+        if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
+        if (const char* e = getenv("VQ_K1_PAIR")) pair = atoi(e);
+        if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
+    }
+};
+inline const TcEnv& tc_env() {
+    static const TcEnv env;
+    return env;
+}
+// Re-read the switches (tests flip them between calls through vq_debug_reload_env; production never does).
+inline void tc_env_reload() { const_cast<TcEnv&>(tc_env()) = TcEnv(); }
+
+// Shared-memory / TMEM layout of one launch, derived from the shape alone.  Returns nullptr when the kernel can run the
+// shape, else the reason (the caller then takes the exact CUDA-core kernel).
+inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
+    using namespace tc;
+    const int Kp = round_up(K, 128), Dp = round_up(D, 64);
+    p.D = D; p.Dp = Dp; p.K = K; p.Kp = Kp;
+    p.n_nt = Kp / TN; p.n_kb = Dp / BKB; p.n_xch = Dp / XCH;
+    p.acc_stages = 2;                                           // one accumulator stage per scan group
+    p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
+    p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
+    const size_t budget = 227 * 1024;
+    const size_t smem_base = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem);
+    // fold the per-code offset into the MMA when the codebook is resident and everything still fits shared memory
+    p.fold = 0; p.cd = CD;
+    if (p.resident && smem_base + handoff_bytes(3) + size_t(p.n_nt) * HN_TILE_BYTES + ACONST_BYTES <= budget) {
+        p.fold = 1;
+        p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES + ACONST_BYTES <= budget ? CD : 3;
+    }
+    if (tc_env().fold == 0) { p.fold = 0; p.cd = CD; }          // A/B switch for measurements
+    p.a_const_col = 512 - 8;
+    // the folded step's constant A slice takes 8 TMEM columns: when the A tile needs all 256 remaining ones (D > 448),
+    // subtract the offset in the scan instead
+    if (p.fold && (p.a_const_col - 2 * TN) / (Dp / 2) < 1) { p.fold = 0; p.cd = CD; }
+    // ||e||^2/2 - B staged in shared memory when it fits next to everything else, else read from global memory
+    p.hn_in_smem = 0;
+    if (!p.fold && Kp <= HN_SMEM_MAX) {
+        if (smem_base + handoff_bytes(CD) + size_t(Kp) * 4 <= budget) p.hn_in_smem = 1;
+        else if (smem_base + handoff_bytes(3) + size_t(Kp) * 4 <= budget) { p.hn_in_smem = 1; p.cd = 3; }
+    }
+    // Three accumulator stages of N = 128 (the tensor core never waits for a scan group to read a stage out) when TMEM
+    // can still hold two converted tiles next to them; the constant operand of the folded step then comes from shared memory.
+    // Measured against the two-stage N = 256 mode (K = 512): 3 % faster at D = 128 on the LJSpeech-like batch (0.0690 vs 0.0713 ms),
+    // equal on equal-length batches, 3.5 % slower at D = 64 -- so it is the default for 64 < D <= 128 only.
+    // VQ_K1_STAGES=2 / 3 overrides (3 only where TMEM allows it).
+    p.const_smem = 0;
+    const bool three_fits = p.fold && p.resident && 3 * TN + 2 * (Dp / 2) <= 512;
+    bool three = three_fits && Dp == 128;
+    if (tc_env().stages > 0) three = three_fits && tc_env().stages == 3;
+    if (three) { p.acc_stages = 3; p.const_smem = 1; }
+    p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
+    if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
+    if (p.acc_stages != 2) p.pair = 0;
+    const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
+    p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
+    if (p.a_bufs < 1) return "emb_width > 512 (the FP16 A operand must fit the TMEM columns next to the accumulators)";
+    p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
+    p.scan_sleep_ns = tc_env().scan_sleep >= 0 ? uint32_t(tc_env().scan_sleep) : 64u;   // (0 .. 250 ns measured within 1 % of each other)
+    smem = smem_base + handoff_bytes(p.cd) +
+           (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES + (p.const_smem ? ACONST_BYTES : 0) : (p.hn_in_smem ? size_t(Kp) * 4 : 0));
+    if (smem > budget) return "shared memory budget exceeded";
+    return nullptr;
+}
+
 // nullptr when the tcgen05 kernel takes this problem, else the reason it does not.
 inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64_t T, int K) {
     if (D > 512) return "emb_width > 512 (the FP16 A operand must fit 256 TMEM columns)";
@@ -958,7 +1029,9 @@ inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64
     if (T >= (int64_t(1) << 31) || N >= (int64_t(1) << 31)) return "dimension too large for a tensor map";
     if (K > (1 << 24)) return "codebook too large";
     if (!tc::encode_tiled_fn()) return "cuTensorMapEncodeTiled is unavailable";
-    return nullptr;
+    tc::Params p;
+    size_t smem = 0;
+    return plan_assign_tc(D, K, p, smem);
 }
 
 inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const float* k, int K, int64_t* idx, float* min_d,
@@ -968,48 +1041,19 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     EncodeTiledFn encode = encode_tiled_fn();
     VQ_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is unavailable");
     Params p;
+    size_t smem = 0;
+    if (const char* why = plan_assign_tc(D, K, p, smem)) return fail("vq_assign (tcgen05 path): %s", why);
+    VQ_REQUIRE(p.Kp == w.Kp && p.Dp == w.Dp, "workspace was carved for another shape");
     p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.list_keys = w.list_keys;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
-    p.N = int(N); p.D = D; p.Dp = w.Dp; p.K = K; p.Kp = w.Kp; p.T = int(T);
+    p.N = int(N); p.T = int(T);
     p.tiles_per_utt = int((T + TM - 1) / TM);
     const int64_t n_tiles = N * p.tiles_per_utt;
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
     p.n_tiles = int(n_tiles);
-    p.n_nt = w.Kp / TN; p.n_kb = w.Dp / BKB; p.n_xch = w.Dp / XCH;
-    p.acc_stages = 2;                                           // one accumulator stage per scan group
-    p.resident = (p.n_nt * p.n_kb <= B_RESIDENT_MAX) ? 1 : 0;
-    p.b_stages = p.resident ? p.n_nt * p.n_kb : B_RING;
-    p.hn_in_smem = w.Kp <= HN_SMEM_MAX ? 1 : 0;
-    // fold the per-code offset into the MMA when the codebook is resident and everything still fits shared memory
-    const size_t smem_base = 1024 + size_t(XS) * X_STAGE_BYTES + size_t(p.b_stages) * B_STAGE_BYTES + sizeof(Smem);
-    p.fold = 0; p.cd = CD;
-    if (p.resident && smem_base + handoff_bytes(3) + size_t(p.n_nt) * HN_TILE_BYTES + ACONST_BYTES <= 227 * 1024) {
-        p.fold = 1;
-        p.cd = smem_base + handoff_bytes(CD) + size_t(p.n_nt) * HN_TILE_BYTES + ACONST_BYTES <= 227 * 1024 ? CD : 3;
-    }
-    if (const char* e = getenv("VQ_K1_FOLD")) { if (atoi(e) == 0) { p.fold = 0; p.cd = CD; } }   // A/B switch for measurements
-    p.a_const_col = 512 - 8;
-    // Three accumulator stages of N = 128 (the tensor core never waits for a scan group to read a stage out) when TMEM
-    // can still hold two converted tiles next to them; the constant operand of the folded step then comes from shared memory.
-    p.const_smem = 0;
-    // Measured against the two-stage N = 256 mode (K = 512): 3 % faster at D = 128 on the LJSpeech-like batch (0.0690 vs 0.0713 ms),
-    // equal on equal-length batches, 3.5 % slower at D = 64 -- so it is the default for 64 < D <= 128 only.
-    // VQ_K1_STAGES=2 / 3 overrides (3 only where TMEM allows it).
-    const bool three_fits = p.fold && p.resident && 3 * TN + 2 * (w.Dp / 2) <= 512;
-    bool three = three_fits && w.Dp == 128;
-    if (const char* e = getenv("VQ_K1_STAGES")) three = three_fits && atoi(e) == 3;
-    if (three) { p.acc_stages = 3; p.const_smem = 1; }
-    p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
-    if (const char* e = getenv("VQ_K1_PAIR")) p.pair = p.pair && atoi(e) != 0;   // A/B switch for measurements
-    if (p.acc_stages != 2) p.pair = 0;
-    const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
-    p.a_bufs = std::min(A_BUFS_MAX, a_cols / (w.Dp / 2));        // converted tiles that fit the remaining TMEM columns
-    p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
-    p.scan_sleep_ns = 64;                                        // (0 .. 250 ns measured within 1 % of each other)
-    if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) p.scan_sleep_ns = uint32_t(atoi(e));
     p.vec_k = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0) ? 1 : 0;
 
-    if (!p.hn_in_smem) {
+    if (!p.fold && !p.hn_in_smem) {
         codebook_offset_kernel<<<std::min(1024, (w.Kp + 255) / 256), 256, 0, stream>>>(w.hn, w.hn_off, K, w.Kp, w.hdr);
         VQ_CUDA_OK(cudaGetLastError());
     }
@@ -1035,15 +1079,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(codebook) failed with CUresult %s%lld", "", (long long)r);
     }
-    const size_t smem = smem_base + handoff_bytes(p.cd) +
-                        (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES + (p.const_smem ? ACONST_BYTES : 0) : (p.hn_in_smem ? size_t(w.Kp) * 4 : 0));
-    VQ_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
-    static bool configured = false;
-    if (!configured) {
-        VQ_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VQ_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    VQ_CUDA_OK(ensure_dynamic_smem(assign_tc_kernel<true>, 227 * 1024));
+    VQ_CUDA_OK(ensure_dynamic_smem(assign_tc_kernel<false>, 227 * 1024));
     const int grid = int(std::min<int64_t>(n_tiles, num_sms()));
     const bool rescore = force_rescore >= 0 ? force_rescore != 0 : (min_d || scalars || dbg);
     if (rescore) assign_tc_kernel<true><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);

@@ -329,13 +329,22 @@ ema_accumulate_global_kernel(const float* __restrict__ x, const int64_t* __restr
     }
 }
 
-// sum of the (already all-reduced) counts -> scalars[VQ_S_COUNT_TOTAL]
-__global__ void __launch_bounds__(256) ema_count_total_kernel(const float* __restrict__ counts, int K, double* scalars) {
+// sum of the (already all-reduced) counts -> scalars[VQ_S_COUNT_TOTAL]; sum of the UPDATED cluster sizes
+// mu k_elem + (1 - mu) counts -> scalars[VQ_S_ELEM_TOTAL] (the `n` of the optional Laplace smoothing)
+__global__ void __launch_bounds__(256) ema_count_total_kernel(const float* __restrict__ counts, const float* __restrict__ k_elem,
+                                                             float mu, float one_minus_mu, int K, double* scalars) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) s += double(counts[c]);
+    double s = 0.0, e = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x) {
+        s += double(counts[c]);
+        e += double(__fadd_rn(__fmul_rn(mu, k_elem[c]), __fmul_rn(one_minus_mu, counts[c])));
+    }
     s = block_sum(s, red);
-    if (threadIdx.x == 0 && s != 0.0) atomicAdd(&scalars[VQ_S_COUNT_TOTAL], s);
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) {
+        if (s != 0.0) atomicAdd(&scalars[VQ_S_COUNT_TOTAL], s);
+        if (e != 0.0) atomicAdd(&scalars[VQ_S_ELEM_TOTAL], e);
+    }
 }
 
 // One warp per code.
@@ -352,6 +361,7 @@ ema_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ k
     const float* sums = stats;
     const float* counts = stats + size_t(K) * D;
     const double total = scalars[VQ_S_COUNT_TOTAL];
+    const double elem_total = scalars[VQ_S_ELEM_TOTAL];
     double ent = 0.0, used = 0.0, usage_n = 0.0, dk = 0.0;
 
     for (int c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < K; c += gridDim.x * warps_per_block) {
@@ -359,8 +369,8 @@ ema_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ k
         // k_elem <- mu k_elem + (1 - mu) n_c                                   (bottleneck.py:80)
         float ke = __fadd_rn(__fmul_rn(mu, k_elem[c]), __fmul_rn(one_minus_mu, n_c));
         float ke_div = ke;
-        if (laplace_eps > 0.f) {
-            float ntot = float(total);
+        if (laplace_eps > 0.f) {      // n = sum of the updated cluster sizes; (k_elem + eps) / (n + K eps) * n
+            const float ntot = float(elem_total);
             ke_div = (ke + laplace_eps) / (ntot + float(K) * laplace_eps) * ntot;
         }
         const bool alive = ke >= threshold;                                     // :81

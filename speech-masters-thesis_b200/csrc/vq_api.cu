@@ -34,11 +34,7 @@ static int launch_gather_v(const float* x, const int64_t* idx, const float* mask
     int Ds;
     int smem = gather_smem_bytes(D, Ds, VEC);
     VQ_REQUIRE(smem <= 200 * 1024, "emb_width too large for the gather tile (max ~750)");
-    static bool configured = false;
-    if (!configured) {
-        VQ_CUDA_OK(cudaFuncSetAttribute(gather_kernel<MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    VQ_CUDA_OK(ensure_dynamic_smem(gather_kernel<MODE, VEC>, 200 * 1024));
     int64_t tiles = N * ((T + G_TT - 1) / G_TT);
     int per_sm = std::max(1, std::min(8, (220 * 1024) / (smem + 1024)));
     int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * per_sm));
@@ -53,11 +49,7 @@ template <int MODE>
 static int launch_gather_async(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,
                                const float* grad_commit, int64_t N, int D, int64_t T, int K, float* out, double* scalars,
                                float* results, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        VQ_CUDA_OK(cudaFuncSetAttribute(gather_async_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GaCfg<MODE>::SMEM)));
-        configured = true;
-    }
+    VQ_CUDA_OK(ensure_dynamic_smem(gather_async_kernel<MODE>, int(GaCfg<MODE>::SMEM)));
     const int64_t units = N * ((T + G_TT - 1) / G_TT) * ((D + GA_DS - 1) / GA_DS);
     const int grid = int(std::min<int64_t>(units, int64_t(num_sms()) * GaCfg<MODE>::CTAS_PER_SM));
     gather_async_kernel<MODE><<<grid, GA_THREADS, GaCfg<MODE>::SMEM, stream>>>(x, idx, mask, k, grad_xq, grad_commit, int(N), D, int(T), K,
@@ -279,11 +271,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
     }
     if (K < (1 << 24) && er_smem_bytes<true>(K) <= ER_DYN_SMEM_MAX) {
         // private [K][64] slab per (row chunk, 64-deep slice); one CTA per SM
-        static bool configured = false;
-        if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ER_DYN_SMEM_MAX));
-            configured = true;
-        }
+        VQ_CUDA_OK(ensure_dynamic_smem(ema_accumulate_runs_kernel<true>, ER_DYN_SMEM_MAX));
         const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
         const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, num_sms() / slices)));
         cudaLaunchConfig_t cfg = {};
@@ -299,11 +287,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
         VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, ema_accumulate_runs_kernel<true>, x, idx, mask, N, int(D), T, K, stats,
                                       (const unsigned char*)flags));
     } else if (K < (1 << 24) && D <= ErCfg<false>::DW) {
-        static bool configured = false;
-        if (!configured) {
-            VQ_CUDA_OK(cudaFuncSetAttribute(ema_accumulate_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ER_DYN_SMEM_MAX));
-            configured = true;
-        }
+        VQ_CUDA_OK(ensure_dynamic_smem(ema_accumulate_runs_kernel<false>, ER_DYN_SMEM_MAX));
         const int grid = int(std::min<int64_t>(tiles_r, num_sms()));
         ema_accumulate_runs_kernel<false><<<grid, ER_THREADS, er_smem_bytes<false>(K), stream>>>(x, idx, mask, N, int(D), T, K, stats, flags);
     } else {
@@ -323,7 +307,7 @@ int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const float* counts = stats + size_t(K) * D;
     int g0 = std::min(64, (K + 255) / 256);
-    ema_count_total_kernel<<<g0, 256, 0, stream>>>(counts, K, scalars);
+    ema_count_total_kernel<<<g0, 256, 0, stream>>>(counts, k_elem, float(mu), float(1.0 - mu), K, scalars);
     VQ_CUDA_OK(cudaGetLastError());
     int grid = std::min((K + 7) / 8, num_sms() * 8);
     // mu and (1 - mu) are rounded to FP32 independently, like `mu * t + (1. - mu) * s` on FP32 tensors
@@ -454,29 +438,38 @@ int vq_encode_host(vq_host_ctx* c, const float* x_host, int64_t N, int64_t T, in
     VQ_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
     VQ_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     int rc = 0;
+    const bool want_sum = sum_min_d_host != nullptr;     // without it the cheaper non-rescoring kernel variant runs
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && !rc) {
+            snprintf(err_buf(), 512, "vq_encode_host: %s failed: %s", what, cudaGetErrorString(e));
+            rc = 1;
+        }
+        return e == cudaSuccess;
+    };
     for (int64_t ci = 0; ci < n_chunks && !rc; ++ci) {
         const int b = int(ci & 1);
         cudaStream_t s = c->streams[b];
         const int64_t n0 = ci * utt_per_chunk, nn = std::min(utt_per_chunk, N - n0);
         if (ci >= 2) {   // the buffer's previous job (scalars read-back included) must be finished
-            if (cudaEventSynchronize(done[b]) != cudaSuccess) { rc = fail("vq_encode_host: event sync failed%s"); break; }
-            total += c->h_scalars[b * VQ_NUM_SCALARS + VQ_S_SUM_MIN_D];
+            if (!cuda_ok(cudaEventSynchronize(done[b]), "cudaEventSynchronize")) break;
+            if (want_sum) total += c->h_scalars[b * VQ_NUM_SCALARS + VQ_S_SUM_MIN_D];
         }
-        cudaMemcpyAsync(c->d_x[b], x_host + n0 * int64_t(c->D) * T, size_t(nn) * bytes_per_utt, cudaMemcpyHostToDevice, s);
-        cudaMemsetAsync(c->d_scalars[b], 0, VQ_NUM_SCALARS * 8, s);
-        rc = vq_assign(c->d_x[b], nn, c->D, T, c->d_k, c->K, c->d_idx[b], nullptr, c->d_scalars[b], c->d_ws[b],
-                       c->ws_bytes, VQ_ALGO_AUTO | (c->prepared[b] ? VQ_ALGO_PREPARED : 0), s);
-        if (rc) break;
+        if (!cuda_ok(cudaMemcpyAsync(c->d_x[b], x_host + n0 * int64_t(c->D) * T, size_t(nn) * bytes_per_utt, cudaMemcpyHostToDevice, s),
+                     "cudaMemcpyAsync(x)")) break;
+        if (want_sum && !cuda_ok(cudaMemsetAsync(c->d_scalars[b], 0, VQ_NUM_SCALARS * 8, s), "cudaMemsetAsync(scalars)")) break;
+        if (vq_assign(c->d_x[b], nn, c->D, T, c->d_k, c->K, c->d_idx[b], nullptr, want_sum ? c->d_scalars[b] : nullptr, c->d_ws[b],
+                      c->ws_bytes, VQ_ALGO_AUTO | (c->prepared[b] ? VQ_ALGO_PREPARED : 0), s)) { rc = 1; break; }
         c->prepared[b] = true;
-        cudaMemcpyAsync(idx_host + n0 * T, c->d_idx[b], size_t(nn) * T * 8, cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(c->h_scalars + b * VQ_NUM_SCALARS, c->d_scalars[b], VQ_NUM_SCALARS * 8, cudaMemcpyDeviceToHost, s);
-        cudaEventRecord(done[b], s);
+        if (!cuda_ok(cudaMemcpyAsync(idx_host + n0 * T, c->d_idx[b], size_t(nn) * T * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(idx)")) break;
+        if (want_sum && !cuda_ok(cudaMemcpyAsync(c->h_scalars + b * VQ_NUM_SCALARS, c->d_scalars[b], VQ_NUM_SCALARS * 8,
+                                                 cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(scalars)")) break;
+        if (!cuda_ok(cudaEventRecord(done[b], s), "cudaEventRecord")) break;
     }
     for (int b = 0; b < 2; ++b) {
         cudaError_t e = cudaStreamSynchronize(c->streams[b]);
         if (e != cudaSuccess && !rc) rc = fail("vq_encode_host: %s", cudaGetErrorString(e));
     }
-    if (!rc) {
+    if (!rc && want_sum) {
         const int64_t tail = std::min<int64_t>(2, n_chunks);
         for (int64_t j = n_chunks - tail; j < n_chunks; ++j) total += c->h_scalars[(j & 1) * VQ_NUM_SCALARS + VQ_S_SUM_MIN_D];
     }

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/vqb200.h"
 
 namespace vq {
@@ -47,6 +49,32 @@ inline int num_sms() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember (kernel, device) pairs, not "done once per
+// process", so a second GPU in the same process gets its opt-in too.
+inline cudaError_t ensure_dynamic_smem_impl(const void* func, int bytes) {
+    struct Entry { const void* func; unsigned long long devices; int bytes; };
+    static Entry table[64];
+    static int n_entries = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* hit = nullptr;
+    for (int i = 0; i < n_entries; ++i)
+        if (table[i].func == func && table[i].bytes == bytes) { hit = &table[i]; break; }
+    if (hit && dev >= 0 && dev < 64 && ((hit->devices >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    if (!hit && n_entries < 64) { table[n_entries] = Entry{func, 0ull, bytes}; hit = &table[n_entries++]; }
+    if (hit && dev >= 0 && dev < 64) hit->devices |= 1ull << dev;
+    return cudaSuccess;
+}
+template <class F>
+inline cudaError_t ensure_dynamic_smem(F* func, int bytes) {
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(func), bytes);
 }
 
 // ------------------------------------------------------------------ device helpers

@@ -27,12 +27,14 @@ def stats_numel(k_bins, emb_width):
     return base + (k_bins * emb_width if fold_restart_rows(k_bins, emb_width) else 0)
 
 
-def allreduce_statistics(stats, k_rand, k_bins, emb_width):
+def allreduce_statistics(stats, k_rand, k_bins, emb_width, async_op=False):
     """SUM the local statistics over all ranks and make rank 0's ``k_rand`` everyone's.  Returns the
-    ``k_rand`` to use (a view into ``stats`` when folded).  No-op for a single process."""
+    ``k_rand`` to use (a view into ``stats`` when folded); with ``async_op`` returns ``(k_rand, work)`` and the
+    collective runs on the backend's own stream until ``work.wait()`` (NCCL: the CURRENT stream then waits for it, the
+    host does not), which is how the module overlaps it with K2.  No-op for a single process."""
     n_ranks, rank = world()
     if n_ranks == 1:
-        return k_rand
+        return (k_rand, None) if async_op else k_rand
     base = k_bins * emb_width + k_bins
     if fold_restart_rows(k_bins, emb_width):
         assert stats.numel() == base + k_bins * emb_width
@@ -40,12 +42,13 @@ def allreduce_statistics(stats, k_rand, k_bins, emb_width):
             stats[base:].copy_(k_rand.reshape(-1))
         else:
             stats[base:].zero_()
-        distributed.all_reduce(stats, distributed.ReduceOp.SUM)
-        return stats[base:].view(k_bins, emb_width)
+        work = distributed.all_reduce(stats, distributed.ReduceOp.SUM, async_op=async_op)
+        k_rand = stats[base:].view(k_bins, emb_width)
+        return (k_rand, work) if async_op else k_rand
     k_rand = k_rand.contiguous()
     distributed.broadcast(k_rand, 0)
-    distributed.all_reduce(stats, distributed.ReduceOp.SUM)
-    return k_rand
+    work = distributed.all_reduce(stats, distributed.ReduceOp.SUM, async_op=async_op)
+    return (k_rand, work) if async_op else k_rand
 
 
 def shard_range(n_items, n_ranks, rank):

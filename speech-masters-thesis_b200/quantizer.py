@@ -36,16 +36,21 @@ def _require_cuda(t, what):
 
 
 class _Workspace:
-    """Per-device scratch for K1 (FP16 codebook image, norms, fallback worklist); grows on demand.  Remembers which
-    codebook it was last prepared for, so a frozen codebook (the generate_vq_dataset loop) is prepared once."""
+    """Scratch for K1 (FP16 codebook image, norms, fallback worklist), one buffer per (device, stream) -- two streams
+    running vq_assign concurrently must not share the fallback worklist; grows on demand.  Remembers which codebook it
+    was last prepared for, so a frozen codebook (the generate_vq_dataset loop) is prepared once."""
     _cache = {}
     _prepared = {}
+
+    @staticmethod
+    def _key(device):
+        return (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
 
     @classmethod
     def get(cls, device, n, t, k, d):
         lib = _lib.load()
         need = int(lib.vq_workspace_bytes(n, t, k, d))
-        key = (device.type, device.index)
+        key = cls._key(device)
         buf = cls._cache.get(key)
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
@@ -60,8 +65,10 @@ class _Workspace:
         """ALGO_PREPARED when `ws` still holds the operands of this very tensor OBJECT at its current version.
 
         The tag lives on the tensor object (an address can be recycled by the caching allocator, an object cannot be
-        confused with its successor) and is matched against the token of the last preparation done in `ws`."""
-        key = (device.type, device.index)
+        confused with its successor) and is matched against the token of the last preparation done in `ws`.
+        Writes that bypass the version counter (``k.data.copy_()``, raw-pointer writes through the C ABI) are not
+        seen: call ``invalidate_prepared()`` after those."""
+        key = cls._key(device)
         tag = getattr(k, "_vqb200_prepared", None)
         if tag is not None and tag == (cls._prepared.get(key), ws.data_ptr(), k._version):
             return _lib.ALGO_PREPARED
@@ -72,6 +79,17 @@ class _Workspace:
         except AttributeError:
             pass
         return 0
+
+
+    @classmethod
+    def invalidate(cls):
+        cls._prepared.clear()
+
+
+def invalidate_prepared():
+    """Forget every prepared-codebook tag (needed only after writing a codebook through ``.data`` or a raw pointer,
+    which does not move the tensor's version counter)."""
+    _Workspace.invalidate()
 
 
 # --------------------------------------------------------------------------------------- raw ops
@@ -140,13 +158,17 @@ class _QuantizeST(torch.autograd.Function):
     """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
 
     @staticmethod
-    def forward(ctx, x, mask, k, algo):
+    def forward(ctx, x, mask, k, algo, after_assign):
         lib = _lib.load()
         n, d, t = x.shape
         kk = k.shape[0]
         scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
         results = torch.zeros(_lib.NUM_RESULTS, dtype=torch.float32, device=x.device)
         idx, _ = assign(x, k, algo)            # indices only; K2 accumulates the `fit` numerator
+        if after_assign is not None:
+            # EMA statistics (K3a) and their all-reduce are issued here, BEFORE K2: the collective then overlaps K2,
+            # which does not depend on it (K1 -> K3a -> {all-reduce || K2} -> K3b)
+            after_assign(idx)
         x_q = torch.empty_like(x)
         if n * t:
             with torch.cuda.device(x.device):
@@ -172,7 +194,7 @@ class _QuantizeST(torch.autograd.Function):
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_bwd(ptr(x), ptr(idx), ptr(mask), ptr(k), ptr(g_xq), ptr(g_commit), ptr(scalars),
                                            n, d, t, k.shape[0], ptr(grad_x), _stream(x)), "vq_gather_st_bwd")
-        return grad_x, None, None, None
+        return grad_x, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- modules
@@ -263,21 +285,38 @@ class BottleneckBlock(nn.Module):
         self.threshold = threshold
 
     # ---- EMA (bottleneck.py:60-90)
-    def _update_k_nct(self, x, x_l, mask, scalars, results, k_rand=None):
+    def _ema_begin(self, x, x_l, mask, k_rand=None):
+        """K3a on the current stream, then the ONE collective of the path, asynchronously.  Returns the pending state for
+        ``_ema_finish``.  With ``rng_parity`` the restart rows need a host round trip (``nonzero`` + CPU ``randperm``);
+        that is deferred to ``_ema_finish`` so K1 / K3a / K2 are all in flight before the host blocks."""
         lib = _lib.load()
         n, d, t = x.shape
         kk = self.k_bins
         with torch.no_grad():
-            if k_rand is None:
-                k_rand = self._restart_rows_nct(x, mask)
             stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):
                 scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=x.device) if mask is not None else None
                 check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), ptr(scratch), _stream(x)),
                       "vq_ema_accumulate")
-            # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
-            # here ONE all-reduce of the packed buffer (see dist.py)
-            k_rand = dist.allreduce_statistics(stats, k_rand, kk, d)
+            pending = dict(stats=stats, k_rand=k_rand, work=None, x=x, mask=mask)
+            if k_rand is None and not self.rng_parity:
+                pending["k_rand"] = self._restart_rows_nct(x, mask)        # device-side draw: no host sync
+            if pending["k_rand"] is not None:
+                # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
+                # here ONE all-reduce of the packed buffer (see dist.py), overlapped with K2
+                pending["k_rand"], pending["work"] = dist.allreduce_statistics(stats, pending["k_rand"], kk, d, async_op=True)
+        return pending
+
+    def _ema_finish(self, pending, scalars, results):
+        lib = _lib.load()
+        stats, k_rand, x = pending["stats"], pending["k_rand"], pending["x"]
+        kk, d = self.k_bins, self.emb_width
+        with torch.no_grad():
+            if k_rand is None:                                               # rng_parity: host RNG replay, after K2 was launched
+                k_rand = self._restart_rows_nct(x, pending["mask"])
+                k_rand, pending["work"] = dist.allreduce_statistics(stats, k_rand, kk, d, async_op=True)
+            if pending["work"] is not None:
+                pending["work"].wait()                                       # the current stream waits for the collective
             k_new = torch.empty_like(self.k)
             used_curr = torch.empty((), dtype=torch.int64, device=x.device)
             if self.k_sum.data_ptr() == self.k.data_ptr():
@@ -290,6 +329,9 @@ class BottleneckBlock(nn.Module):
             self.k = k_new          # rebind like the reference does (:82); autograd may still hold the old tensor
         return dict(entropy=results[_lib.R_ENTROPY], used_curr=used_curr, usage=results[_lib.R_USAGE],
                     dk=results[_lib.R_DK])
+
+    def _update_k_nct(self, x, x_l, mask, scalars, results, k_rand=None):
+        return self._ema_finish(self._ema_begin(x, x_l, mask, k_rand), scalars, results)
 
     def update_k(self, x, x_l):
         """bottleneck.py:60-90 with the reference's signature: ``x`` [M, D] valid rows, ``x_l`` [M] codes."""
@@ -373,9 +415,11 @@ class BottleneckBlock(nn.Module):
             with torch.no_grad():
                 self._set_codebook(self._restart_rows_nct(x.detach(), mask))      # init_k (:179-180)
         k = self.k if self.k.dtype == torch.float32 else self.k.float()
-        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo)
+        pending = []
+        hook = (lambda x_l: pending.append(self._ema_begin(x.detach(), x_l, mask))) if update_k else None
+        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook)
         if update_k:
-            update_metrics = self._update_k_nct(x.detach(), x_l, mask, scalars, results)
+            update_metrics = self._ema_finish(pending[0], scalars, results)
         else:
             update_metrics = {}
         return x_l, x_q, commit_loss, dict(fit=results[_lib.R_FIT], **update_metrics)
