@@ -205,7 +205,7 @@ def run_b200(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    signal.alarm(env_int("VQ_BENCH_TIMEOUT", 540))      # a wedged collective must not eat the GPU lease
+    signal.alarm(env_int("VQ_BENCH_TIMEOUT", 900))      # a wedged collective must not eat the GPU lease
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")

@@ -2,8 +2,8 @@
 // Replaces bottleneck.py:92-100 (NCT flatten -- fused: tiles are read straight from NCT),
 // :129-134 (distance + min) and the `fit` numerator of :140.
 //
-// Two uses: (1) any shape the tcgen05 kernel does not take (D > 512, unaligned T, ...);
-// (2) LIST mode: the exact re-scan of the few rows the tcgen05 kernel flags as unsafe.
+// Two kernels: (1) assign_simt_kernel, for any shape the tcgen05 kernel does not take (D > 512, unaligned T, ...);
+// (2) assign_list_kernel, the exact re-scan of the few frames the tcgen05 kernel flags as unsafe.
 #pragma once
 #include "vq_common.cuh"
 #include "k1_prepare.cuh"
@@ -14,54 +14,29 @@ constexpr int S_BM = 128;   // rows (frames) per tile
 constexpr int S_BN = 64;    // codes per inner tile
 constexpr int S_BK = 16;    // depth per step
 
-// LIST = false: tile i covers frames [t0, t0+128) of utterance n (tiles never straddle utterances).
-// LIST = true : tile i covers row_list[i*128 .. i*128+127]; the count lives in device memory.  The code range is split
-//               over blockIdx.y so that a short list still fills the machine; the partial (distance, index) minima
-//               meet in list_keys[] through a 64-bit atomicMin whose ordering is exactly "smaller distance, then lower
-//               index" (torch.min's tie rule); the last block to finish writes the results.
-template <bool LIST>
+// Tile i covers frames [t0, t0+128) of utterance n (tiles never straddle utterances).
 __global__ void __launch_bounds__(256)
 assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
                    const float* __restrict__ k, const float* __restrict__ ee, int K,
-                   int64_t* __restrict__ idx, float* __restrict__ min_d, double* __restrict__ scalars,
-                   const int* __restrict__ row_list, AssignHeader* __restrict__ hdr,
-                   unsigned long long* __restrict__ list_keys) {
+                   int64_t* __restrict__ idx, float* __restrict__ min_d, double* __restrict__ scalars) {
     __shared__ __align__(16) float Xs[S_BK][S_BM];
     __shared__ __align__(16) float Es[S_BK][S_BN + 4];
     __shared__ long long row_off[S_BM];      // offset of x[n, 0, t] for each tile row, -1 when out of range
     __shared__ double red[32];
 
-    // (LIST runs as a programmatic dependent of the tcgen05 kernel: nothing that kernel wrote may be read before this)
-    if (LIST) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t tiles_per_utt = (T + S_BM - 1) / S_BM;
-    const int64_t n_rows_list = LIST ? int64_t(*reinterpret_cast<volatile int*>(&hdr->unsafe_count)) : 0;
-    const int64_t n_tiles = LIST ? (n_rows_list + S_BM - 1) / S_BM : N * tiles_per_utt;
+    const int64_t n_tiles = N * tiles_per_utt;
     const bool vec_k = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
     double tile_sum = 0.0;
-    // codes [c_lo, c_hi) for this block (LIST mode: a 64-code-aligned slice per blockIdx.y)
-    int c_lo = 0, c_hi = K;
-    if (LIST) {
-        const int per = ((K + int(gridDim.y) - 1) / int(gridDim.y) + S_BN - 1) / S_BN * S_BN;
-        c_lo = min(K, int(blockIdx.y) * per);
-        c_hi = min(K, c_lo + per);            // empty slices skip the tile loop but still take a ticket below
-    }
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles && c_lo < c_hi; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
         if (tid < S_BM) {
             long long off = -1;
-            if (LIST) {
-                int64_t j = tile * S_BM + tid;
-                if (j < n_rows_list) {
-                    int64_t r = row_list[j];
-                    off = (r / T) * int64_t(D) * T + (r % T);
-                }
-            } else {
-                int64_t n = tile / tiles_per_utt, t = (tile % tiles_per_utt) * S_BM + tid;
-                if (t < T) off = n * int64_t(D) * T + t;
-            }
+            int64_t n = tile / tiles_per_utt, t = (tile % tiles_per_utt) * S_BM + tid;
+            if (t < T) off = n * int64_t(D) * T + t;
             row_off[tid] = off;
         }
         __syncthreads();
@@ -72,7 +47,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
         for (int i = 0; i < 8; ++i) { xx[i] = 0.f; bd[i] = __int_as_float(0x7f800000); bi[i] = 0x7fffffff; }
 
-        for (int c0 = c_lo; c0 < c_hi; c0 += S_BN) {
+        for (int c0 = 0; c0 < K; c0 += S_BN) {
             float acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -119,7 +94,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
                     }
-                    if (c0 == c_lo) {
+                    if (c0 == 0) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) xx[i] = fmaf(a[i], a[i], xx[i]);
                     }
@@ -130,7 +105,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int c = c0 + tx * 4 + j;
-                if (c < c_hi) {
+                if (c < K) {
                     float e2 = ee[c];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -155,60 +130,147 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
             for (int i = 0; i < 8; ++i) {
                 int r = ty * 8 + i;
                 if (row_off[r] >= 0) {
-                    if (LIST) {
-                        // orderable bits of the distance (monotone for all finite floats and +inf), then the index
-                        const unsigned b = __float_as_uint(bd[i]);
-                        const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                        const unsigned long long key = (static_cast<unsigned long long>(ord) << 32) | unsigned(bi[i]);
-                        atomicMin(&list_keys[tile * S_BM + r], key);
-                    } else {
-                        const int64_t row = (tile / tiles_per_utt) * T + (tile % tiles_per_utt) * S_BM + r;
-                        idx[row] = bi[i] == 0x7fffffff ? 0 : bi[i];
-                        if (min_d) min_d[row] = bd[i];
-                        tile_sum += double(bd[i]);
-                    }
+                    const int64_t row = (tile / tiles_per_utt) * T + (tile % tiles_per_utt) * S_BM + r;
+                    idx[row] = bi[i] == 0x7fffffff ? 0 : bi[i];
+                    if (min_d) min_d[row] = bd[i];
+                    tile_sum += double(bd[i]);
                 }
             }
         }
     }
-    if (LIST) {
-        if (n_rows_list == 0) return;         // common case (speech-like latents): nothing to do, nothing to re-arm
-        // the last block to finish writes the results of the whole list (one thread per listed row) and re-arms the header
-        __shared__ bool is_last;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            const unsigned ticket = atomicAdd(&hdr->list_ticket, 1u);
-            is_last = ticket == gridDim.x * gridDim.y - 1;
-        }
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        double sum = 0.0;
-        for (int64_t j = tid; j < n_rows_list; j += blockDim.x) {
-            const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&list_keys[j]);
-            const unsigned ord = unsigned(key >> 32);
-            const unsigned b = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
-            const float d = __uint_as_float(b);
-            const unsigned ci = unsigned(key & 0xffffffffu);
-            const int row = row_list[j];
-            idx[row] = ci == 0x7fffffffu ? 0 : int64_t(ci);
-            if (min_d) min_d[row] = d;
-            sum += double(d);
-        }
-        sum = block_sum(sum, red);
-        if (tid == 0) {
-            if (scalars && n_rows_list) {
-                atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
-                atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n_rows_list));
-            }
-            hdr->unsafe_count = 0;            // ready for the next vq_assign on this workspace (no memset needed)
-            hdr->list_ticket = 0;
-        }
-        return;
-    }
     double s = block_sum(tile_sum, red);
     if (tid == 0 && scalars && s != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-scan of the frames the tcgen05 kernel could not prove safe (bottleneck.py:129-134 for those rows, FP32, lowest
+// index on ties like torch.min).  The tcgen05 pass leaves, per listed frame, a 32-bit mask: bit (16 g + j) set means "the
+// exact winner may be a code of scan group g (code tile parity) in residue chain j (code % 16 == j)"; every other code was
+// proven out of reach by its FP16 score (see finish() in k1_assign_tc.cuh).  Typically two chains survive: K/16 codes
+// instead of K -- the re-scan of 2 % of a batch went from 0.11 ms (all codes, 128-row tiles, 64-bit atomics) to ~0.01 ms.
+//   one WARP per listed frame; the frame's D values live in registers (lane = depth quad), a candidate code row is one
+//   coalesced 16-byte load per lane, eight candidates are reduced together with a transposing butterfly (9 shuffles).
+// Launched as a programmatic dependent of the tcgen05 kernel; the frame count lives in device memory.
+constexpr int L_WARPS = 8;
+constexpr int L_MAXQ = 4;        // depth quads per lane: D <= 512
+
+template <bool VEC>
+__global__ void __launch_bounds__(L_WARPS * 32)
+assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
+                   const float* __restrict__ ee, int K, int n_code_tiles, int64_t* __restrict__ idx, float* __restrict__ min_d,
+                   double* __restrict__ scalars, const int* __restrict__ row_list, const uint32_t* __restrict__ row_mask,
+                   AssignHeader* __restrict__ hdr) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // nothing the tcgen05 kernel wrote may be read before this
+    const int n_list = *reinterpret_cast<volatile int*>(&hdr->unsafe_count);
+    if (n_list == 0) return;                               // common case (speech-like latents): nothing to do, nothing to re-arm
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sum = 0.0;
+    for (int j = blockIdx.x * L_WARPS + warp; j < n_list; j += gridDim.x * L_WARPS) {
+        const int64_t row = row_list[j];
+        const uint32_t mask = row_mask[j];
+        const float* src = x + (row / T) * int64_t(D) * T + (row % T);
+        // this lane's slice of the frame: depths 4 (lane + 32 q) .. + 3   (VEC)   or   lane + 32 i   (scalar)
+        float xr[4 * L_MAXQ];
+        float xx = 0.f;
+#pragma unroll
+        for (int q = 0; q < L_MAXQ; ++q)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = VEC ? 4 * (lane + 32 * q) + u : lane + 32 * (4 * q + u);
+                const float v = d < D ? __ldg(src + int64_t(d) * T) : 0.f;
+                xr[4 * q + u] = v;
+                xx = fmaf(v, v, xx);
+            }
+        xx = warp_sum(xx);
+        float bd = __int_as_float(0x7f800000);
+        int bi = 0x7fffffff;
+        for (int g = 0; g < 2; ++g) {
+            uint32_t mg = (mask >> (16 * g)) & 0xFFFFu;
+            while (mg) {
+                const int res = __ffs(mg) - 1;
+                mg &= mg - 1;
+                for (int nt = g; nt < n_code_tiles; nt += 2) {
+                    // the eight codes of chain `res` in code tile nt: c = 128 nt + 16 b + res
+                    float part[8];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int c = nt * 128 + 16 * b + res;
+                        float acc = 0.f;
+                        if (c < K) {
+                            const float* er = k + size_t(c) * D;
+                            if (VEC) {
+#pragma unroll
+                                for (int q = 0; q < L_MAXQ; ++q)
+                                    if (4 * (lane + 32 * q) < D) {
+                                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + lane + 32 * q);
+                                        acc = fmaf(xr[4 * q + 0], e4.x, acc); acc = fmaf(xr[4 * q + 1], e4.y, acc);
+                                        acc = fmaf(xr[4 * q + 2], e4.z, acc); acc = fmaf(xr[4 * q + 3], e4.w, acc);
+                                    }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4 * L_MAXQ; ++i)
+                                    if (lane + 32 * i < D) acc = fmaf(xr[i], __ldg(er + lane + 32 * i), acc);
+                            }
+                        }
+                        part[b] = acc;
+                    }
+                    // transposing butterfly: afterwards every lane holds the full dot product of code b = (lane >> 2) & 7
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const bool hi = (lane & 16) != 0;
+                        const float keep = hi ? part[b + 4] : part[b], give = hi ? part[b] : part[b + 4];
+                        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const bool hi = (lane & 8) != 0;
+                        const float keep = hi ? part[b + 2] : part[b], give = hi ? part[b] : part[b + 2];
+                        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+                    }
+                    {
+                        const bool hi = (lane & 4) != 0;
+                        const float keep = hi ? part[1] : part[0], give = hi ? part[0] : part[1];
+                        part[0] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+                    }
+                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
+                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+                    const int b_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    const int c = nt * 128 + 16 * b_mine + res;
+                    if (c < K) argmin_take(bd, bi, ref_distance(xx, part[0], __ldg(ee + c)), c);
+                }
+            }
+        }
+        // combine the lanes (lanes sharing a code hold identical values)
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmin_take(bd, bi, od, oi);
+        }
+        if (lane == 0) {
+            idx[row] = bi == 0x7fffffff ? 0 : bi;
+            if (min_d) min_d[row] = bd;
+            sum += double(bd);
+        }
+    }
+    // the last block to finish re-arms the header for the next vq_assign on this workspace (no memset needed)
+    sum = block_sum(sum, red);
+    if (threadIdx.x == 0) {
+        if (scalars) {
+            if (sum != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
+            if (blockIdx.x == 0) atomicAdd(&scalars[VQ_S_UNSAFE_ROWS], double(n_list));
+        }
+        __threadfence();
+        const unsigned ticket = atomicAdd(&hdr->list_ticket, 1u);
+        is_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        hdr->unsafe_count = 0;
+        hdr->list_ticket = 0;
+    }
 }
 
 }  // namespace vq

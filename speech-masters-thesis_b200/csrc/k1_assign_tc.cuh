@@ -67,7 +67,7 @@ constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared m
 
 struct Params {
     const float* x; const float* k; const float* ee; const float* hn; const float* hn_off;
-    AssignHeader* hdr; int* unsafe_rows; unsigned long long* list_keys;
+    AssignHeader* hdr; int* unsafe_rows; uint32_t* unsafe_mask;
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
     int N, D, Dp, K, Kp, T;
@@ -78,6 +78,7 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
+    int dual_issue;          // two MMA issuer warps (even / odd code tiles): resident codebook, N = 128 batches only
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
 
@@ -107,7 +108,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // SLEEP_NS > 0 backs off with nanosleep between probes (used where a few hundred ns of wake-up latency is harmless).
-constexpr int REGS_ISSUER = 40, REGS_FRONT = 120, REGS_SCAN = 176;    // 4*40 + 4*120 + 8*176 = 2048 = 16 warps x 128
+constexpr int REGS_ISSUER = 48, REGS_FRONT = 112, REGS_SCAN = 176;    // 4*48 + 4*112 + 8*176 = 2048 = 16 warps x 128
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -370,13 +371,15 @@ __device__ __forceinline__ void issue_batch_n(int n_kb, uint32_t d_tmem, uint32_
             p.trace[(e) * p.trace_tiles + int(it_)] = clock64();                                  \
     } while (0)
 
-struct __align__(16) Cand { uint32_t k1, k2; int c1; int pad; };   // per frame, per scan group: best key, runner-up key, best's code
+struct __align__(16) Cand { uint32_t k1, k2; int c1; uint32_t chains; };   // per frame, per scan group: best key, runner-up key, best's code,
+                                                                          // residue chains (bit j: column % 16 == j) that may hold the exact winner
 
 struct __align__(16) Smem {           // control block placed after the data stages
     uint64_t x_full[XS], x_empty[XS];
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
+    float err_c[4];      // e_norm_max, e_err_max, 1.2e-7 Dp e_norm_max, 4 ulp(t): the per-frame FP16 error bound's constants (scan groups)
 };
 // after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
 // for their back stage); then either the folded -(||e||^2/2 - B) tiles or the FP32 offset vector.
@@ -406,10 +409,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
-        for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
+        for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), p.dual_issue ? 2 : 1); }
         for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 4); }
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ctl->err_c[0] = e_norm_max;
+        ctl->err_c[1] = __uint_as_float(p.hdr->e_err_max_bits);
+        ctl->err_c[2] = 1.2e-7f * float(p.Dp) * e_norm_max;
+        ctl->err_c[3] = 4.f * ks.ulp;
     }
     // the folded offset must be representable as three FP16 terms; otherwise (absurdly large norms) every frame falls back
     const bool fold_ok = ks.offset < 3.0e4f;
@@ -518,10 +525,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
         }
     } else if (warp == W_MMA) {
-        // ============================================================ MMA issuer
+        // ============================================================ MMA issuer(s)
+        // dual_issue (resident codebook, N = 128 batches): warp W_MMA issues the even code tiles, warp W_ALLOC the odd ones.
+        // A tcgen05.commit is followed by the next batch's barrier probe in the same warp, and that probe only returns
+        // once the commit has retired, i.e. after the batch's last MMA has FINISHED (measured: ~200 cycles between the
+        // commit and the next probe's return, tools/tc_timeline.py) -- a single issuer therefore lets the tensor pipe run
+        // dry at every batch boundary.  With two issuers one warp's drain overlaps the other warp's MMAs.
         reg_dec<REGS_ISSUER>();
         {
             const bool leader = elect_one();
+            const bool dual = p.dual_issue != 0;
             uint32_t qa = 0, it = 0;
             Ring ra, rb;                                      // A buffers; streaming B stages
             // loop-invariant operands of the resident fast path
@@ -568,6 +581,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                     } else {
                         for (int nt = 0; nt < n_nt; ++nt, ++qa, rs.next(acc_stages)) {
+                            if (dual && (nt & 1)) continue;             // odd code tiles: the second issuer (warp W_ALLOC)
                             const uint32_t st = rs.i, sph = rs.ph;
                             mbar_spin(smem_u32(&ctl->acc_empty[st]), sph ^ 1);
                             tc_fence_after();
@@ -679,6 +693,51 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 VQ_TRACE(2, it);
             }
         }
+    } else if (warp == W_ALLOC) {
+        // ============================================================ second MMA issuer (dual_issue): the odd code tiles
+        reg_dec<REGS_ISSUER>();
+        if (p.dual_issue) {
+            const bool leader = elect_one();
+            Ring ra, rs;
+            const uint64_t bd0 = b_desc_base(smem_u32(bs_base));
+            const uint64_t kb_stride = uint64_t(p.n_nt) * uint64_t(B_STAGE_BYTES >> 4);
+            const uint64_t hd0 = hn_desc(smem_u32(hn_b));
+            const uint32_t a_const = tmem + uint32_t(p.a_const_col);
+            const uint64_t ac_desc = aconst_desc(smem_u32(hn_b + size_t(p.n_nt) * HN_TILE_BYTES));
+            const bool const_smem = p.const_smem != 0, fold = p.fold != 0;
+            const uint32_t acc_stages = uint32_t(p.acc_stages), a_bufs = uint32_t(p.a_bufs);
+            const int n_kb = p.n_kb, n_nt = p.n_nt;
+            bool first_tile = true;
+            for (int tile = first; tile < p.n_tiles; tile += step, ra.next(a_bufs), first_tile = false) {
+                const uint32_t a = ra.i;
+                if (first_tile) {
+                    // the B tiles are still landing: warp W_MMA issues all of the first tile.  This commit has no MMA of
+                    // this thread to wait for and arrives at once.
+                    for (int nt = 0; nt < n_nt; ++nt) rs.next(acc_stages);
+                    if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
+                    continue;
+                }
+                mbar_spin(smem_u32(&ctl->a_full[a]), ra.ph);
+                tc_fence_after();
+                const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
+                for (int nt = 0; nt < n_nt; ++nt, rs.next(acc_stages)) {
+                    if (!(nt & 1)) continue;
+                    const uint32_t st = rs.i;
+                    mbar_spin(smem_u32(&ctl->acc_empty[st]), rs.ph ^ 1);
+                    tc_fence_after();
+                    if (leader) {
+                        issue_batch_n<IDESC>(n_kb, tmem + st * TN, a_tmem, bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4), kb_stride);
+                        if (fold) {
+                            if (const_smem) tc_mma_ss(tmem + st * TN, ac_desc, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
+                            else tc_mma_ts(tmem + st * TN, a_const, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
+                        }
+                        tc_commit(smem_u32(&ctl->acc_full[st]));
+                    }
+                    __syncwarp();
+                }
+                if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
+            }
+        }
     } else if (warp < 4) {
         // ============================================================ front/back group (thread == frame)
         reg_dec<REGS_FRONT>();
@@ -708,6 +767,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             wfin.advance(step, p.tiles_per_utt);
             const bool in_tile = t < p.T;
             bool unsafe = false;
+            uint32_t cand_mask = 0xFFFFFFFFu;                 // bits 0-15: residue chains of scan group 0 (even code tiles), 16-31: group 1
             const int64_t row = int64_t(n) * p.T + t;
             if (in_tile) {
                 const float xx = st.x, rr = st.y;
@@ -718,7 +778,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 const uint32_t kbound = __vimax3_u32(min(ca.k1, cc.k1), ca.k2, cc.k2);
                 const float t_best = __uint_as_float(kbest), t_bound = __uint_as_float(kbound);
                 const float xn = sqrtf(xx);
-                const float acc_err = 1.2e-7f * float(p.Dp) * xn * e_norm_max;              // FP32 accumulation of D products
+                const float acc_err = (1.2e-7f * float(p.Dp) * e_norm_max) * xn;            // FP32 accumulation of D products
                 const float err = sqrtf(rr) * e_norm_max + xn * e_err_max + acc_err + 4.f * ks.ulp;   // FP16 rounding of x and E, roundings of t
                 // the key order is only meaningful while every score of this frame stays inside the key range
                 const bool in_range = (xn * e_norm_max + 0.51f * e_norm_max * e_norm_max) < 0.98f * ks.half_range;
@@ -754,7 +814,17 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     // both approximate scores carry at most `err`; the difference of two t is exact
                     safe = (t_best - t_bound) > 2.f * err;
                 }
-                safe = safe && in_range && c1 < p.K && (!p.fold || fold_ok);
+                const bool keys_ok = in_range && (!p.fold || fold_ok);
+                safe = safe && keys_ok && c1 < p.K;
+                if (keys_ok) {
+                    // Pruning for the exact re-scan: a code c can only be the exact winner if its approximate score is within
+                    // 2 err of the approximate best (s16(c) >= s(c) - err >= s(best) - err >= s16(best) - 2 err); each scan
+                    // group flagged the residue chains whose maximum clears its own (lower or equal) threshold, and a group
+                    // whose best is out of reach contributes nothing.
+                    const float reach = t_best - 2.f * err;
+                    cand_mask = (__uint_as_float(ca.k1) >= reach ? (ca.chains & 0xFFFFu) : 0u) |
+                                (__uint_as_float(cc.k1) >= reach ? (cc.chains << 16) : 0u);
+                }
 #if VQ_EXPERIMENT & 4                     /* timing experiment: never take the fallback */
                 safe = true;
 #endif
@@ -777,7 +847,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 if (unsafe) {
                     const int pos = base + __popc(m & ((1u << lane) - 1u));
                     p.unsafe_rows[pos] = int(row);
-                    p.list_keys[pos] = ~0ull;                    // identity of the re-scan's atomicMin
+                    p.unsafe_mask[pos] = cand_mask;              // which codes the exact re-scan has to look at
                 }
             }
         };
@@ -846,9 +916,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; ++j) ch[j] = 0u;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa, rs.next(acc_stages)) {
-                // The two scan groups take ALTERNATE code tiles, so one group's TMEM loads and barrier waits overlap the
-                // other group's arithmetic on the same scheduler instead of both stalling together.
-                if ((qa & 1u) != uint32_t(wg)) continue;
+                // The two scan groups take ALTERNATE code tiles (group 0 the even ones), so one group's TMEM loads and barrier
+                // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
+                if ((uint32_t(nt) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
                 // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
                 // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
@@ -906,13 +976,28 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             int res = 0;                                           // the winner's residue: the chain that holds the maximum
 #pragma unroll
             for (int j = 1; j < 16; ++j) res = ch[j] == r1 ? j : res;
-            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1 + res; c.pad = 0;
+            // Residue chains of this group that can hold the exact winner (used by the exact re-scan if the frame turns out
+            // unsafe): normally only the best's own chain; when the group's runner-up is within 2 err of its best, every chain
+            // whose maximum is.  (rowstat of this tile was written by the front group before the tile's MMAs were issued.)
+            uint32_t chains = 1u << res;
+            {
+                const float2 st = rowstat[cb * TM + r];
+                const float4 ec = *reinterpret_cast<const float4*>(ctl->err_c);
+                const float xn = sqrtf(st.x);
+                const float acc_err = ec.z * xn;
+                const float err = sqrtf(st.y) * ec.x + xn * ec.y + acc_err + ec.w;    // == finish()'s err
+                const float reach = __uint_as_float(r1) - 2.f * err;
+                if (!(__uint_as_float(r2) < reach)) {
+                    chains = 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) chains |= (__uint_as_float(ch[j]) >= reach) ? (1u << j) : 0u;
+                }
+            }
+            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1 + res; c.chains = chains;
             cand[(cb * 2 + wg) * TM + r] = c;
             mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
             if (warp == 4) VQ_TRACE(9, it);
         }
-    } else {
-        reg_dec<REGS_ISSUER>();                                     // W_ALLOC: idle until the end
     }
 
     tc_fence_before();
@@ -951,14 +1036,15 @@ inline EncodeTiledFn encode_tiled_fn() {
 }  // namespace tc
 
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
-// VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
+// VQ_K1_SCAN_SLEEP=<ns>, VQ_K1_DUAL=0 (single MMA issuer).  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, dual = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
         if (const char* e = getenv("VQ_K1_PAIR")) pair = atoi(e);
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
+        if (const char* e = getenv("VQ_K1_DUAL")) dual = atoi(e);
     }
 };
 inline const TcEnv& tc_env() {
@@ -1010,6 +1096,8 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
+    p.dual_issue = (p.resident && !p.pair && p.n_nt >= 2) ? 1 : 0;
+    if (tc_env().dual >= 0) p.dual_issue = p.dual_issue && tc_env().dual != 0;
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
     if (p.a_bufs < 1) return "emb_width > 512 (the FP16 A operand must fit the TMEM columns next to the accumulators)";
@@ -1044,7 +1132,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     size_t smem = 0;
     if (const char* why = plan_assign_tc(D, K, p, smem)) return fail("vq_assign (tcgen05 path): %s", why);
     VQ_REQUIRE(p.Kp == w.Kp && p.Dp == w.Dp, "workspace was carved for another shape");
-    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.list_keys = w.list_keys;
+    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.unsafe_mask = w.unsafe_mask;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.T = int(T);
     p.tiles_per_utt = int((T + TM - 1) / TM);

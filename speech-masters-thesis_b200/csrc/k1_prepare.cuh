@@ -23,8 +23,8 @@ struct AssignWorkspace {
     float* hn;            // [Kp]  ||e||^2 / 2, huge beyond K
     float* hn_off;        // [Kp]  ||e||^2 / 2 - B (key offset), written only for codebooks too large for shared memory
     __half* eb;           // [Kp][Dp] FP16 image, zero padded
-    int* unsafe_rows;     // [N*T]
-    unsigned long long* list_keys;   // [N*T] packed (distance, index) minima of the exact re-scan, by list position
+    int* unsafe_rows;     // [N*T] frames the tcgen05 kernel could not prove safe
+    uint32_t* unsafe_mask;           // [N*T] per listed frame: residue chains (column % 16) x scan group whose codes the exact re-scan visits
     int Kp, Dp;
     size_t bytes;
 };
@@ -44,7 +44,7 @@ inline AssignWorkspace carve_workspace(void* base, int64_t rows, int K, int D) {
     w.hn_off = reinterpret_cast<float*>(p + off);                  off += align256(size_t(w.Kp) * 4);
     w.eb = reinterpret_cast<__half*>(p + off);              off += align256(size_t(w.Kp) * w.Dp * 2);
     w.unsafe_rows = reinterpret_cast<int*>(p + off);               off += align256(size_t(rows) * 4);
-    w.list_keys = reinterpret_cast<unsigned long long*>(p + off);  off += align256(size_t(rows) * 8);
+    w.unsafe_mask = reinterpret_cast<uint32_t*>(p + off);          off += align256(size_t(rows) * 4);
     w.bytes = off;
     return w;
 }

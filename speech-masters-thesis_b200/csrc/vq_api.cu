@@ -178,29 +178,34 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         if (launch_assign_tc(x, N, int(D), T, k, K, idx, min_d, scalars, w, stream, dbg, trace, trace_tiles,
                              trace ? (dbg != nullptr) : -1)) return 1;
         prof_mark(pslot, 2, stream);
-        // exact re-scan of the rows whose FP16 shortlist could not be proven safe (the count lives on the device):
-        // list tiles x code slices, so that a handful of rows still spreads over the machine
-        const int splits = std::max(1, std::min(16, (K + S_BN - 1) / S_BN));
-        const int gx = int(std::min<int64_t>(std::max(1, 4 * num_sms() / splits), (N * T + S_BM - 1) / S_BM));
+        // exact re-scan of the frames whose FP16 shortlist could not be proven safe (the count lives on the device), one
+        // warp per frame over the codes the tcgen05 pass could not rule out.
         // Programmatic dependent launch: the kernel is set up while the main kernel still runs (which signals
         // launch_dependents right after its prologue) and waits on griddepcontrol.wait before it reads the count, so the
         // usual empty-worklist case costs ~3 us less than a serialised launch.
+        const int gx = int(std::min<int64_t>(4 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(gx, splits);
-        cfg.blockDim = dim3(256);
+        cfg.gridDim = dim3(gx);
+        cfg.blockDim = dim3(L_WARPS * 32);
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = (g_prof.on && pslot >= 0) ? 0 : 1;          // (event records between the two kernels serialise them anyway)
-        VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_simt_kernel<true>, x, N, int(D), T, k, (const float*)w.ee, K, idx, min_d, scalars,
-                                      (const int*)w.unsafe_rows, w.hdr, w.list_keys));
+        const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
+        const int n_code_tiles = w.Kp / 128;
+        if (vec) {
+            VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_list_kernel<true>, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d,
+                                          scalars, (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr));
+        } else {
+            VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_list_kernel<false>, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d,
+                                          scalars, (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr));
+        }
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));
-        assign_simt_kernel<false><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars,
-                                                            nullptr, nullptr, nullptr);
+        assign_simt_kernel<<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars);
         VQ_CUDA_OK(cudaGetLastError());
         prof_mark(pslot, 2, stream);
     }

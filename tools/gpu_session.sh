@@ -1,0 +1,18 @@
+#!/bin/bash
+# one GPU-box session: tests, bench, K1 timeline + A/B switches; everything lands in gpurun_out/
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+for v in 1 0; do echo "VQ_K1_DUAL=$v: $(VQ_K1_DUAL=$v python bench.py --steps 50 --warmup 5 --profile-only 2>&1 | tail -1)"; done | tee gpurun_out/ab.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'],'k1_ms',d['roofline']['kernel_ms'])
+print('sustained',d['roofline']['sustained'])
+print('gaussian',{k:v for k,v in d['gaussian'].items() if k!='index_match'})
+print('index',d['index_match'])
+print('training',d['training_path'])
+PY
+timeout 300 python tools/tc_timeline.py > gpurun_out/tl.log 2>&1
