@@ -108,7 +108,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // SLEEP_NS > 0 backs off with nanosleep between probes (used where a few hundred ns of wake-up latency is harmless).
-constexpr int REGS_ISSUER = 48, REGS_FRONT = 112, REGS_SCAN = 176;    // 4*48 + 4*112 + 8*176 = 2048 = 16 warps x 128
+constexpr int REGS_ISSUER = 40, REGS_FRONT = 120, REGS_SCAN = 176;    // 4*40 + 4*120 + 8*176 = 2048 = 16 warps x 128
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
