@@ -379,7 +379,7 @@ struct __align__(16) Smem {           // control block placed after the data sta
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
-    float err_c[4];      // e_norm_max, e_err_max, 1.2e-7 Dp e_norm_max, 4 ulp(t): the per-frame FP16 error bound's constants (scan groups)
+    alignas(16) float err_c[4];      // e_norm_max, e_err_max, 1.2e-7 Dp e_norm_max, 4 ulp(t): the per-frame FP16 error bound's constants (scan groups)
 };
 // after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
 // for their back stage); then either the folded -(||e||^2/2 - B) tiles or the FP32 offset vector.
