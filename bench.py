@@ -471,6 +471,9 @@ def run_b200(args):
     k_sum, k_elem, k_new = kd.clone(), torch.ones(K_BINS, device=dev), torch.empty_like(kd)
     k2_fwd = timed(lambda: lib.vq_gather_st_fwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K_BINS,
                                                 x_q.data_ptr(), scalars.data_ptr(), res.data_ptr(), stream))
+    stats_f = torch.zeros(K_BINS * EMB + K_BINS, device=dev)
+    k2_fused = timed(lambda: lib.vq_gather_st_fwd_ema(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K_BINS,
+                                                      x_q.data_ptr(), scalars.data_ptr(), res.data_ptr(), stats_f.data_ptr(), stream))
     k2_bwd = timed(lambda: lib.vq_gather_st_bwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), x_q.data_ptr(),
                                                 g_commit.data_ptr(), scalars.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
     k2_dec = timed(lambda: lib.vq_decode(idx.data_ptr(), kd.data_ptr(), n, d, t, K_BINS, x_q.data_ptr(), stream))
@@ -485,6 +488,7 @@ def run_b200(args):
 
     rooflines = [
         hbm_line("K2 vq_gather_st_fwd", k2_fwd, rows * (8 * EMB + 12)),
+        hbm_line("K2+K3a vq_gather_st_fwd_ema (fused; what the training forward runs)", k2_fused, rows * (8 * EMB + 12) + 4 * K_BINS * (EMB + 1)),
         hbm_line("K2 vq_gather_st_bwd", k2_bwd, rows * (12 * EMB + 12)),
         hbm_line("K2 vq_decode", k2_dec, rows * (4 * EMB + 8)),
         hbm_line("K3a vq_ema_accumulate", k3_acc, valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1)),

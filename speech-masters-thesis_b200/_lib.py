@@ -35,6 +35,9 @@ SIGNATURES = {
                                  _c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_int]),
     "vq_gather_st_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "vq_gather_st_fwd_ema_supported": (_c_int, [_c_i64, _c_i64, _c_int]),
+    "vq_gather_st_fwd_ema": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int,
+                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "vq_gather_st_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                   _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p]),
     "vq_decode": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p]),

@@ -151,6 +151,20 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
         if (++spins > SPIN_LIMIT) __trap();
     } while (!mbar_try_wait(bar, parity));
 }
+// dual_issue ordering.  The two issuers share the accumulator stages, and an mbarrier parity wait is only meaningful while the
+// waiter is at most ONE phase ahead: before issuer X waits for the release of the stage batch q will use, the other issuer
+// must have got past ITS wait for that stage's previous use (batch q - acc_stages) -- otherwise X could read "parity done"
+// off a barrier that is still two releases behind and overwrite an accumulator nobody has read yet.
+__device__ __forceinline__ void issuer_publish(uint32_t* slot, uint32_t count) {
+    *reinterpret_cast<volatile uint32_t*>(slot) = count;
+    __threadfence_block();
+}
+__device__ __forceinline__ void issuer_wait_for(const uint32_t* slot, uint32_t at_least) {
+    uint32_t spins = 0;
+    while (*reinterpret_cast<const volatile uint32_t*>(slot) < at_least)
+        if (++spins > (SPIN_LIMIT << 6)) __trap();
+    __threadfence_block();
+}
 // One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
 // asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
 // compiler wrap every tcgen05.mma / TMA in an ELECT + R2UR.BROADCAST loop, ~190 cycles per instruction).
@@ -379,6 +393,7 @@ struct __align__(16) Smem {           // control block placed after the data sta
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
+    uint32_t issued[2];  // dual_issue: code-tile batches each MMA issuer has got past the accumulator-empty wait of (its own count)
     alignas(16) float err_c[4];      // e_norm_max, e_err_max, 1.2e-7 Dp e_norm_max, 4 ulp(t): the per-frame FP16 error bound's constants (scan groups)
 };
 // after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
@@ -413,6 +428,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 4); }
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ctl->issued[0] = ctl->issued[1] = 0u;
         ctl->err_c[0] = e_norm_max;
         ctl->err_c[1] = __uint_as_float(p.hdr->e_err_max_bits);
         ctl->err_c[2] = 1.2e-7f * float(p.Dp) * e_norm_max;
@@ -583,7 +599,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         for (int nt = 0; nt < n_nt; ++nt, ++qa, rs.next(acc_stages)) {
                             if (dual && (nt & 1)) continue;             // odd code tiles: the second issuer (warp W_ALLOC)
                             const uint32_t st = rs.i, sph = rs.ph;
+                            if (dual && qa >= acc_stages) issuer_wait_for(&ctl->issued[(qa - acc_stages) & 1u], ((qa - acc_stages) >> 1) + 1u);
                             mbar_spin(smem_u32(&ctl->acc_empty[st]), sph ^ 1);
+                            if (dual) issuer_publish(&ctl->issued[0], (qa >> 1) + 1u);
                             tc_fence_after();
                             VQ_TRACE_NT(10, it, nt);
                             if (leader) {
@@ -689,6 +707,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     if (leader) tc_commit(smem_u32(&ctl->acc_full[s]));
                     VQ_TRACE_NT(11, it, nt);
                 }
+                if (dual) {                                   // (first tile: this warp issued the odd code tiles too)
+                    issuer_publish(&ctl->issued[0], qa >> 1);
+                    issuer_publish(&ctl->issued[1], qa >> 1);
+                }
                 if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
                 VQ_TRACE(2, it);
             }
@@ -708,22 +730,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const uint32_t acc_stages = uint32_t(p.acc_stages), a_bufs = uint32_t(p.a_bufs);
             const int n_kb = p.n_kb, n_nt = p.n_nt;
             bool first_tile = true;
+            uint32_t qa = 0;
             for (int tile = first; tile < p.n_tiles; tile += step, ra.next(a_bufs), first_tile = false) {
                 const uint32_t a = ra.i;
                 if (first_tile) {
                     // the B tiles are still landing: warp W_MMA issues all of the first tile.  This commit has no MMA of
                     // this thread to wait for and arrives at once.
-                    for (int nt = 0; nt < n_nt; ++nt) rs.next(acc_stages);
+                    for (int nt = 0; nt < n_nt; ++nt, ++qa) rs.next(acc_stages);
                     if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
                     continue;
                 }
                 mbar_spin(smem_u32(&ctl->a_full[a]), ra.ph);
                 tc_fence_after();
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
-                for (int nt = 0; nt < n_nt; ++nt, rs.next(acc_stages)) {
+                for (int nt = 0; nt < n_nt; ++nt, ++qa, rs.next(acc_stages)) {
                     if (!(nt & 1)) continue;
                     const uint32_t st = rs.i;
+                    if (qa >= acc_stages) issuer_wait_for(&ctl->issued[(qa - acc_stages) & 1u], ((qa - acc_stages) >> 1) + 1u);
                     mbar_spin(smem_u32(&ctl->acc_empty[st]), rs.ph ^ 1);
+                    issuer_publish(&ctl->issued[1], (qa >> 1) + 1u);
                     tc_fence_after();
                     if (leader) {
                         issue_batch_n<IDESC>(n_kb, tmem + st * TN, a_tmem, bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4), kb_stride);
@@ -1096,7 +1121,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
-    p.dual_issue = (p.resident && !p.pair && p.n_nt >= 2) ? 1 : 0;
+    p.dual_issue = (p.resident && !p.pair && p.n_nt >= 2 && p.n_nt % 2 == 0) ? 1 : 0;   // (even: code-tile parity == batch parity)
     if (tc_env().dual >= 0) p.dual_issue = p.dual_issue && tc_env().dual != 0;
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns

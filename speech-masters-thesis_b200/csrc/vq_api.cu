@@ -5,6 +5,7 @@
 #include "k1_assign_simt.cuh"
 #include "k1_assign_tc.cuh"
 #include "k2_gather.cuh"
+#include "k2_fused_ema.cuh"
 #include "k3_ema.cuh"
 
 #include <algorithm>
@@ -236,6 +237,29 @@ int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, cons
     VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
     return launch_gather<GM_FWD>(x, idx, mask, k, nullptr, nullptr, N, int(D), T, K, x_q, scalars, results,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int vq_gather_st_fwd_ema_supported(int64_t D, int64_t T, int K) {
+    return (K > 0 && K <= FE_KMAX && D > 0 && D <= FE_DMAX && T > 0 && T % 4 == 0 && T < (int64_t(1) << 31)) ? 1 : 0;
+}
+
+int vq_gather_st_fwd_ema(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,
+                         int64_t T, int K, float* x_q, double* scalars, float* results, float* stats, void* stream) {
+    if (check_shape(N, D, T, K)) return 1;
+    VQ_REQUIRE(scalars && results && stats, "scalars/results/stats must not be null");
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && idx && k && x_q, "null pointer");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    VQ_REQUIRE(vq_gather_st_fwd_ema_supported(D, T, K), "fused forward + EMA needs K <= 512, D <= 128, T % 4 == 0");
+    VQ_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_q) & 15) == 0, "x / x_q must be 16-byte aligned");
+    const int64_t units = N * ((T + G_TT - 1) / G_TT);
+    VQ_REQUIRE(units < (int64_t(1) << 31), "too many tiles");
+    VQ_CUDA_OK(ensure_dynamic_smem(gather_fwd_ema_kernel, int(FE_SMEM)));
+    const int grid = int(std::min<int64_t>(units, num_sms()));
+    gather_fwd_ema_kernel<<<grid, FE_THREADS, FE_SMEM, static_cast<cudaStream_t>(stream)>>>(x, idx, mask, k, int(N), int(D), int(T), K, x_q,
+                                                                                          scalars, results, stats, (unsigned int)grid);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int vq_gather_st_bwd(const float* x, const int64_t* idx, const float* mask, const float* k, const float* grad_xq,

@@ -158,7 +158,7 @@ class _QuantizeST(torch.autograd.Function):
     """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
 
     @staticmethod
-    def forward(ctx, x, mask, k, algo, after_assign):
+    def forward(ctx, x, mask, k, algo, after_assign, fused_stats):
         lib = _lib.load()
         n, d, t = x.shape
         kk = k.shape[0]
@@ -170,7 +170,12 @@ class _QuantizeST(torch.autograd.Function):
             # which does not depend on it (K1 -> K3a -> {all-reduce || K2} -> K3b)
             after_assign(idx)
         x_q = torch.empty_like(x)
-        if n * t:
+        if n * t and fused_stats is not None:
+            # K2 and K3a in one pass over x (EMA accumulators in tensor memory): K1 -> K2+K3a -> all-reduce -> K3b
+            with torch.cuda.device(x.device):
+                check(lib.vq_gather_st_fwd_ema(ptr(x), ptr(idx), ptr(mask), ptr(k), n, d, t, kk, ptr(x_q), ptr(scalars),
+                                               ptr(results), ptr(fused_stats), _stream(x)), "vq_gather_st_fwd_ema")
+        elif n * t:
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_fwd(ptr(x), ptr(idx), ptr(mask), ptr(k), n, d, t, kk, ptr(x_q), ptr(scalars),
                                            ptr(results), _stream(x)), "vq_gather_st_fwd")
@@ -194,7 +199,7 @@ class _QuantizeST(torch.autograd.Function):
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_bwd(ptr(x), ptr(idx), ptr(mask), ptr(k), ptr(g_xq), ptr(g_commit), ptr(scalars),
                                            n, d, t, k.shape[0], ptr(grad_x), _stream(x)), "vq_gather_st_bwd")
-        return grad_x, None, None, None, None
+        return grad_x, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- modules
@@ -214,6 +219,7 @@ class BottleneckBlock(nn.Module):
         # host time at 300 k frames).  False: K rows are drawn on the device (with replacement, no sync); same distribution,
         # different random stream.
         self.rng_parity = rng_parity
+        self.fuse_ema = None                  # None: K2 + K3a fused whenever the shape allows it; False: separate kernels
         self.reset_k()
 
     # ---- state (bottleneck.py:20-24)
@@ -285,7 +291,15 @@ class BottleneckBlock(nn.Module):
         self.threshold = threshold
 
     # ---- EMA (bottleneck.py:60-90)
-    def _ema_begin(self, x, x_l, mask, k_rand=None):
+    def _fuse_ema_ok(self, x):
+        """K2 + K3a in one kernel (EMA accumulators in tensor memory) when the shape allows it; ``fuse_ema`` = False keeps
+        them apart (K3a before K2, so the all-reduce overlaps K2), None = fuse whenever possible."""
+        if self.fuse_ema is False or x.numel() == 0 or x.data_ptr() % 16:
+            return False
+        n, d, t = x.shape
+        return bool(_lib.load().vq_gather_st_fwd_ema_supported(d, t, self.k_bins))
+
+    def _ema_begin(self, x, x_l, mask, k_rand=None, stats=None):
         """K3a on the current stream, then the ONE collective of the path, asynchronously.  Returns the pending state for
         ``_ema_finish``.  With ``rng_parity`` the restart rows need a host round trip (``nonzero`` + CPU ``randperm``);
         that is deferred to ``_ema_finish`` so K1 / K3a / K2 are all in flight before the host blocks."""
@@ -293,11 +307,12 @@ class BottleneckBlock(nn.Module):
         n, d, t = x.shape
         kk = self.k_bins
         with torch.no_grad():
-            stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
-            with torch.cuda.device(x.device):
-                scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=x.device) if mask is not None else None
-                check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), ptr(scratch), _stream(x)),
-                      "vq_ema_accumulate")
+            if stats is None:                    # (else: the fused K2 + K3a kernel already accumulated into `stats`)
+                stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
+                with torch.cuda.device(x.device):
+                    scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=x.device) if mask is not None else None
+                    check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), ptr(scratch), _stream(x)),
+                          "vq_ema_accumulate")
             pending = dict(stats=stats, k_rand=k_rand, work=None, x=x, mask=mask)
             if k_rand is None and not self.rng_parity:
                 pending["k_rand"] = self._restart_rows_nct(x, mask)        # device-side draw: no host sync
@@ -415,10 +430,15 @@ class BottleneckBlock(nn.Module):
             with torch.no_grad():
                 self._set_codebook(self._restart_rows_nct(x.detach(), mask))      # init_k (:179-180)
         k = self.k if self.k.dtype == torch.float32 else self.k.float()
-        pending = []
-        hook = (lambda x_l: pending.append(self._ema_begin(x.detach(), x_l, mask))) if update_k else None
-        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook)
+        pending, hook, fused_stats = [], None, None
+        if update_k and self._fuse_ema_ok(x):
+            fused_stats = torch.zeros(dist.stats_numel(self.k_bins, self.emb_width), dtype=torch.float32, device=x.device)
+        elif update_k:
+            hook = lambda x_l: pending.append(self._ema_begin(x.detach(), x_l, mask))
+        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook, fused_stats)
         if update_k:
+            if fused_stats is not None:
+                pending.append(self._ema_begin(x.detach(), x_l, mask, stats=fused_stats))
             update_metrics = self._ema_finish(pending[0], scalars, results)
         else:
             update_metrics = {}

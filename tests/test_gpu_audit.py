@@ -123,6 +123,55 @@ def test_two_streams_do_not_share_a_workspace(vq):
         audit(xs[i], code, outs[i])
 
 
+@pytest.mark.parametrize("shape", [(64, 128, 512, True), (5, 96, 300, False), (3, 32, 40, True), (2, 128, 512, False)],
+                         ids=lambda s: f"N{s[0]}_D{s[1]}_K{s[2]}")
+def test_fused_forward_ema_matches_separate_kernels(vq, shape):
+    """vq_gather_st_fwd_ema (K2 + K3a in one pass, per-code accumulators in tensor memory) against the two separate kernels
+    and against the oracle's one-hot GEMM statistics: x_q bit-equal, counts exact, sums 1e-5."""
+    n, D, K, clustered = shape
+    gen = torch.Generator().manual_seed(n * 1000 + D)
+    code = torch.randn(K, D, generator=gen)
+    lengths = O.ljspeech_like_lengths(n, gen) // 4 * 4
+    lengths[-1] = 8                                               # a nearly empty utterance: many fully padded tiles
+    x, mask = O.synthetic_batch(lengths, D, gen, codebook=code if clustered else None)
+    xd, md, kd = x.to(DEV), mask.to(DEV), code.to(DEV)
+    outs = []
+    for fuse in (None, False):
+        blk = vq.BottleneckBlock(K, D, 0.99, 1.0).to(DEV)
+        blk.fuse_ema = fuse
+        blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 2, torch.full((K,), 2.0, device=DEV), True
+        blk.train()
+        assert blk._fuse_ema_ok(xd) == (fuse is None)
+        torch.manual_seed(3)
+        x_l, x_q, commit, metrics = blk(xd, md, update_k=True)
+        outs.append((x_l.cpu(), x_q.cpu(), float(commit), blk.k.cpu(), blk.k_sum.cpu(), blk.k_elem.cpu(),
+                     {k: float(v) for k, v in metrics.items()}))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2]
+    assert torch.equal(a[5], b[5])                                                   # counts: exact
+    assert torch.allclose(a[4], b[4], rtol=1e-5, atol=1e-5) and torch.allclose(a[3], b[3], rtol=1e-5, atol=1e-5)
+    for key in a[6]:
+        assert abs(a[6][key] - b[6][key]) <= 1e-5 * abs(b[6][key]) + 1e-6, key
+    # and against the oracle statistics (bottleneck.py:64-68) through the raw entry point
+    rows, _, valid = O.flatten_nct(x, mask)
+    s_sum, s_elem = O.local_statistics(rows[valid], a[0].reshape(-1)[valid], K)
+    lib = vq._lib.load()
+    stats = torch.zeros(K * D + K, device=DEV)
+    x_q = torch.empty_like(xd)
+    scalars = torch.zeros(16, dtype=torch.float64, device=DEV)
+    res = torch.zeros(8, device=DEV)
+    idx = a[0].to(DEV)
+    rc = lib.vq_gather_st_fwd_ema(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, D, x.shape[2], K, x_q.data_ptr(),
+                                  scalars.data_ptr(), res.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.vq_last_error()
+    assert torch.equal(stats[K * D:].cpu(), s_elem)
+    assert torch.allclose(stats[:K * D].view(K, D).cpu(), s_sum, rtol=1e-5, atol=2e-5)
+    assert torch.equal(x_q.cpu(), a[1])
+    # shapes the fused kernel does not take are refused, not mangled
+    assert lib.vq_gather_st_fwd_ema_supported(128, 1024, 513) == 0 and lib.vq_gather_st_fwd_ema_supported(129, 1024, 512) == 0
+    assert lib.vq_gather_st_fwd_ema_supported(128, 1023, 512) == 0 and lib.vq_gather_st_fwd_ema_supported(128, 1024, 512) == 1
+
+
 def test_laplace_smoothing_formula(vq):
     """Opt-in smoothing: k = k_sum / ((k_elem + eps) / (n + K eps) * n) with n = sum of the UPDATED k_elem."""
     gen = torch.Generator().manual_seed(2)
