@@ -227,26 +227,53 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
         // ---- EMA statistics of this unit (bottleneck.py:64-68): runs of equal codes -> one TMEM column update each
         if (warp == 15) sort_unit((it + 1) & (GA_RING - 1), sorted + ((it + 1) & 1) * G_TT);   // next unit's keys (its indices landed a wait ago)
         if (quad * 32 < dn) {
+            // Runs are found lane-parallel (two ballots over the sorted keys give a 64-bit mask of run heads) and this warp
+            // takes runs sub, sub + 4, ...: at most 16.  Their sums stay in registers; the 16 TMEM columns are then read,
+            // updated and written back as ONE batch, so the tensor-memory round trip is paid once per tile, not per run.
             const uint32_t* keys = sorted + (it & 1) * G_TT;
             const float* col = S + (quad * 32 + lane) * FE_XS;        // this lane's depth row of the x tile
-            int i = 0, run = 0;
-            while (i < G_TT) {
-                const uint32_t key = keys[i];
-                if (key == 0xFFFFFFFFu) break;                        // sorted: no more valid frames
-                const uint32_t code = key >> 8;
-                int j = i + 1;
-                while (j < G_TT && (keys[j] >> 8) == code) ++j;
-                if ((run & 3) == sub) {
-                    float a = 0.f;
-                    for (int f = i; f < j; ++f) a += col[keys[f] & 255u];
-                    float v;
-                    fe_tmem_ld1(tq + code, v);
-                    fe_tmem_st1(tq + code, v + a);
-                    if (quad == 0 && lane == 0) s_cnt[code] += float(j - i);
+            const uint32_t k0 = keys[lane], k1 = keys[32 + lane];
+            const bool v0 = k0 != 0xFFFFFFFFu, v1 = k1 != 0xFFFFFFFFu;
+            const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+            const uint32_t k0_last = __shfl_sync(0xffffffffu, k0, 31);
+            const bool h0 = v0 && (lane == 0 || (k0 >> 8) != (p0 >> 8));
+            const bool h1 = v1 && ((k1 >> 8) != ((lane == 0 ? k0_last : p1) >> 8));
+            unsigned long long heads = (unsigned long long)__ballot_sync(0xffffffffu, h0) |
+                                       ((unsigned long long)__ballot_sync(0xffffffffu, h1) << 32);
+            const int nvalid = __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, v1));
+            for (int sk = 0; sk < sub; ++sk) heads &= heads - 1;      // runs 0 .. sub-1 belong to the other warps of this quadrant
+            float a[16];
+            uint32_t cc[16];
+            int len[16];
+            int nr = 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                a[r] = 0.f; cc[r] = 0u; len[r] = 0;
+                if (heads) {                                          // (warp-uniform)
+                    const int sb = __ffsll((long long)heads) - 1;
+                    heads &= heads - 1;
+                    const int eb = heads ? __ffsll((long long)heads) - 1 : nvalid;
+                    heads &= heads - 1; heads &= heads - 1; heads &= heads - 1;      // the next three runs are other warps'
+                    const uint32_t ks = sb < 32 ? __shfl_sync(0xffffffffu, k0, sb) : __shfl_sync(0xffffffffu, k1, sb - 32);
+                    float acc = 0.f;
+                    for (int f = sb; f < eb; ++f) {
+                        const uint32_t kf = f < 32 ? __shfl_sync(0xffffffffu, k0, f) : __shfl_sync(0xffffffffu, k1, f - 32);
+                        acc += col[kf & 255u];
+                    }
+                    a[r] = acc; cc[r] = ks >> 8; len[r] = eb - sb; nr = r + 1;
                 }
-                ++run;
-                i = j;
             }
+            uint32_t v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r < nr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[r]) : "r"(tq + cc[r]) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r < nr) {
+                    fe_tmem_st1(tq + cc[r], __uint_as_float(v[r]) + a[r]);
+                    if (quad == 0 && lane == 0) s_cnt[cc[r]] += float(len[r]);
+                }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         gather_st((it + 1) % FE_NST, ev);

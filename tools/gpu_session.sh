@@ -3,7 +3,8 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-for v in 1 0; do echo "VQ_K1_DUAL=$v: $(VQ_K1_DUAL=$v python bench.py --steps 50 --warmup 5 --profile-only 2>&1 | tail -1)"; done | tee gpurun_out/ab.log
+timeout 300 python tools/list_debug.py 2>&1 | tail -2 | tee gpurun_out/list_debug.log
+for v in 1 0 1 0; do echo "VQ_K1_DUAL=$v: $(VQ_K1_DUAL=$v python bench.py --steps 50 --warmup 5 --profile-only 2>&1 | tail -1)"; done | tee gpurun_out/ab.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench.err
 python - <<'PY'
@@ -13,6 +14,6 @@ print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'],'k1_
 print('sustained',d['roofline']['sustained'])
 print('gaussian',{k:v for k,v in d['gaussian'].items() if k!='index_match'})
 print('index',d['index_match'])
+for r in d['rooflines']: print(r['kernel'], round(r['ms'],4), round(r['frac'],3))
 print('training',d['training_path'])
 PY
-timeout 300 python tools/tc_timeline.py > gpurun_out/tl.log 2>&1
