@@ -115,8 +115,8 @@ int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, cons
 
 /* K2 forward + K3a in one pass over x (training forward): everything vq_gather_st_fwd does, plus the per-code sums and
  * counts of the valid frames ADDED into stats [K*D + K] (what vq_ema_accumulate computes; bottleneck.py:64-68), so x is read
- * from HBM once instead of twice.  The per-code FP32 accumulators live in the SM's tensor memory (128 lanes = depth, 512
- * columns = code), hence K <= 512, D <= 128; also T % 4 == 0 and 16-byte aligned x / x_q.  vq_gather_st_fwd_ema_supported
+ * from HBM once instead of twice.  Each thread block keeps a private [K][64] slab of per-code sums in shared memory, hence
+ * K <= 512 (any D <= 512, in 64-deep slices); also T % 4 == 0 and 16-byte aligned x / x_q.  vq_gather_st_fwd_ema_supported
  * returns 1 when the shape qualifies (the caller otherwise uses vq_gather_st_fwd + vq_ema_accumulate). */
 int vq_gather_st_fwd_ema_supported(int64_t emb_width, int64_t t_frames, int k_bins);
 int vq_gather_st_fwd_ema(const float* x, const int64_t* idx, const float* mask, const float* k,

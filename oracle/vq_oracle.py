@@ -245,6 +245,47 @@ def forward(state: CodebookState, x: torch.Tensor, mask: torch.Tensor, update_k:
     return x_l2, x_q * mask_nct, commit, dict(fit=fit, **metrics)
 
 
+# --------------------------------------------------------------------------- grouped (phoneme-conditioned) quantiser
+def align_tokens(x_id: torch.Tensor, attn: torch.Tensor) -> torch.Tensor:
+    """models/vqtts/bottleneck.py:28: the token id of every frame, ``x_id @ attn`` -> [b, ty] int64.
+
+    As shipped the reference multiplies a [b, tx] id matrix with the [b, tx, ty] alignment, which broadcasts to
+    [b, b, ty] and only reshapes for b == 1 (the authors train with batch size 1, scripts/train_vqvae.sh:14).  For b == 1
+    this is that expression; for b > 1 it is the evident per-utterance intent."""
+    return torch.matmul(x_id.to(attn.dtype).unsqueeze(1), attn).squeeze(1).long()
+
+
+def grouped_forward(state: CodebookState, y_enc: torch.Tensor, x_id: torch.Tensor, attn: torch.Tensor, n_vocab: int,
+                    l_bins: int, training: bool = True, update_k: bool = True, k_rand: Optional[torch.Tensor] = None):
+    """models/vqtts/bottleneck.py:19-77 ``Bottleneck.forward`` (K = n_vocab * l_bins codes, frame j only competes among
+    the l_bins codes of its aligned token).  Returns (q_rel [b, ty] int64, y_d [b, c, ty], commit_loss, metrics).
+    Quirks reproduced: init_k sees ALL rows (padded ones too, :35-36); the EMA update runs iff ``training`` (the
+    ``update_k`` argument only gates init, :35,63); ``fit`` carries the (NT,)x(NT,1) broadcast, i.e. sum_all(min_d)/l_bins."""
+    b, tx, ty = attn.shape
+    c = y_enc.shape[1]
+    mask = attn.sum(1).reshape(b * ty, 1)                                        # :25
+    valid = mask.bool().flatten()
+    tok = align_tokens(x_id, attn).reshape(b * ty)                               # :28,32
+    rows = y_enc.permute(0, 2, 1).reshape(b * ty, c)                             # :31
+    if update_k and not state.init:
+        init_codebook(state, rows.detach(), k_rand)                              # :35-36
+    with torch.no_grad():
+        k = state.k.reshape(n_vocab, l_bins, c)[tok]                             # :39-40  [b*ty, l, c]
+        dist = (torch.sum(rows.unsqueeze(1) ** 2, dim=-1) - 2 * torch.bmm(rows.unsqueeze(1), k.transpose(1, 2)).squeeze(1)
+                + torch.sum(k ** 2, dim=-1))                                     # :44-49
+        min_d, q_rel = torch.min(dist, dim=-1)                                   # :52
+        fit = torch.sum(min_d) / l_bins                                          # :54 (== sum(min_d * mask) / (mask.sum() * l) through the broadcast)
+        q_abs = (tok * l_bins + q_rel).long()                                    # :58
+        y_d = gather(q_abs, state.k)                                             # :60
+    metrics = {}
+    if training:
+        metrics = update_codebook(state, rows[valid].detach(), q_abs[valid], k_rand)    # :62-63
+    commit = torch.norm(y_d[valid].detach() - rows[valid]) ** 2 / (mask.sum() * c)      # :68
+    y_st = rows + (y_d - rows).detach()                                          # :71
+    y_out = (y_st * mask).reshape(b, ty, c).permute(0, 2, 1)                     # :74
+    return q_rel.reshape(b, ty), y_out, commit, dict(fit=fit, **metrics)
+
+
 def backward_wrt_x(x: torch.Tensor, mask: torch.Tensor, x_l: torch.Tensor, k: torch.Tensor,
                    grad_xq: torch.Tensor, grad_commit: float) -> torch.Tensor:
     """Closed form of the autograd contract: only x receives gradient,

@@ -151,10 +151,86 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 //   one WARP per listed frame; the frame's D values live in registers (lane = depth quad), a candidate code row is one
 //   coalesced 16-byte load per lane, eight candidates are reduced together with a transposing butterfly (9 shuffles).
 // Launched as a programmatic dependent of the tcgen05 kernel; the frame count lives in device memory.
-constexpr int L_WARPS = 8;
-constexpr int L_MAXQ = 4;        // depth quads per lane: D <= 512
+constexpr int L_WARPS = 4;
 
-template <bool VEC>
+// One chain segment = the eight codes c = 128 nt + 16 b + res (b = 0..7) of residue chain `res` in code tile `nt`.
+// dot8 leaves in every lane the partial dot products of its depth slice with the eight codes (loads first, then FMAs).
+template <bool VEC, int MAXQ>
+__device__ __forceinline__ void list_dot8(const float* __restrict__ k, int D, int K, int nt, int res, int lane,
+                                          const float (&xr)[4 * MAXQ], float (&part)[8]) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int c = nt * 128 + 16 * b + res;
+        float acc = 0.f;
+        if (c < K) {
+            const float* er = k + size_t(c) * D;
+            if (VEC) {
+#pragma unroll
+                for (int q = 0; q < MAXQ; ++q)
+                    if (4 * (lane + 32 * q) < D) {
+                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + lane + 32 * q);
+                        acc = fmaf(xr[4 * q + 0], e4.x, acc); acc = fmaf(xr[4 * q + 1], e4.y, acc);
+                        acc = fmaf(xr[4 * q + 2], e4.z, acc); acc = fmaf(xr[4 * q + 3], e4.w, acc);
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4 * MAXQ; ++i)
+                    if (lane + 32 * i < D) acc = fmaf(xr[i], __ldg(er + lane + 32 * i), acc);
+            }
+        }
+        part[b] = acc;
+    }
+}
+// transposing butterfly: afterwards every lane holds the full dot product of code b = 4 bit4 + 2 bit3 + bit2 of its lane id
+__device__ __forceinline__ float list_reduce8(float (&part)[8], int lane) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const bool hi = (lane & 16) != 0;
+        const float keep = hi ? part[b + 4] : part[b], give = hi ? part[b] : part[b + 4];
+        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const bool hi = (lane & 8) != 0;
+        const float keep = hi ? part[b + 2] : part[b], give = hi ? part[b] : part[b + 2];
+        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+    {
+        const bool hi = (lane & 4) != 0;
+        const float keep = hi ? part[1] : part[0], give = hi ? part[0] : part[1];
+        part[0] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
+    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+    return part[0];
+}
+// walks the (group, chain, code tile) segments a mask selects, in increasing group / chain / tile order
+struct ListWalk {
+    uint32_t mask;
+    int n_code_tiles, g, res, nt;
+    __device__ __forceinline__ ListWalk(uint32_t m, int n) : mask(m), n_code_tiles(n), g(-1), res(0), nt(1 << 30) {}
+    __device__ __forceinline__ bool next() {
+        nt += 2;
+        while (nt >= n_code_tiles) {
+            // next chain of this group, else the next group
+            uint32_t mg = g >= 0 ? (mask >> (16 * g)) & 0xFFFFu & ~((2u << res) - 1u) : 0u;
+            while (mg == 0u) {
+                if (++g > 1) return false;
+                mg = (mask >> (16 * g)) & 0xFFFFu;
+                res = -1;
+                if (mg) break;
+            }
+            res = __ffs(mg) - 1;
+            nt = g;
+        }
+        return true;
+    }
+};
+
+// The per-frame work is a chain of dependent L2 / DRAM round trips (frame id -> x -> code rows -> ||e||^2), so the kernel is
+// latency-bound: two segments are evaluated per step (16 code rows and both norms in flight at once) and frames are spread
+// one per warp over as many resident warps as the register budget allows (MAXQ = 1 for D <= 128).
+template <bool VEC, int MAXQ>
 __global__ void __launch_bounds__(L_WARPS * 32)
 assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
                    const float* __restrict__ ee, int K, int n_code_tiles, int64_t* __restrict__ idx, float* __restrict__ min_d,
@@ -166,16 +242,18 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     const int n_list = *reinterpret_cast<volatile int*>(&hdr->unsafe_count);
     if (n_list == 0) return;                               // common case (speech-like latents): nothing to do, nothing to re-arm
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const float inf = __int_as_float(0x7f800000);
     double sum = 0.0;
     for (int j = blockIdx.x * L_WARPS + warp; j < n_list; j += gridDim.x * L_WARPS) {
         const int64_t row = row_list[j];
         const uint32_t mask = row_mask[j];
         const float* src = x + (row / T) * int64_t(D) * T + (row % T);
         // this lane's slice of the frame: depths 4 (lane + 32 q) .. + 3   (VEC)   or   lane + 32 i   (scalar)
-        float xr[4 * L_MAXQ];
+        float xr[4 * MAXQ];
         float xx = 0.f;
 #pragma unroll
-        for (int q = 0; q < L_MAXQ; ++q)
+        for (int q = 0; q < MAXQ; ++q)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int d = VEC ? 4 * (lane + 32 * q) + u : lane + 32 * (4 * q + u);
@@ -184,62 +262,24 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
                 xx = fmaf(v, v, xx);
             }
         xx = warp_sum(xx);
-        float bd = __int_as_float(0x7f800000);
+        float bd = inf;
         int bi = 0x7fffffff;
-        for (int g = 0; g < 2; ++g) {
-            uint32_t mg = (mask >> (16 * g)) & 0xFFFFu;
-            while (mg) {
-                const int res = __ffs(mg) - 1;
-                mg &= mg - 1;
-                for (int nt = g; nt < n_code_tiles; nt += 2) {
-                    // the eight codes of chain `res` in code tile nt: c = 128 nt + 16 b + res
-                    float part[8];
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const int c = nt * 128 + 16 * b + res;
-                        float acc = 0.f;
-                        if (c < K) {
-                            const float* er = k + size_t(c) * D;
-                            if (VEC) {
-#pragma unroll
-                                for (int q = 0; q < L_MAXQ; ++q)
-                                    if (4 * (lane + 32 * q) < D) {
-                                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + lane + 32 * q);
-                                        acc = fmaf(xr[4 * q + 0], e4.x, acc); acc = fmaf(xr[4 * q + 1], e4.y, acc);
-                                        acc = fmaf(xr[4 * q + 2], e4.z, acc); acc = fmaf(xr[4 * q + 3], e4.w, acc);
-                                    }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 4 * L_MAXQ; ++i)
-                                    if (lane + 32 * i < D) acc = fmaf(xr[i], __ldg(er + lane + 32 * i), acc);
-                            }
-                        }
-                        part[b] = acc;
-                    }
-                    // transposing butterfly: afterwards every lane holds the full dot product of code b = (lane >> 2) & 7
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const bool hi = (lane & 16) != 0;
-                        const float keep = hi ? part[b + 4] : part[b], give = hi ? part[b] : part[b + 4];
-                        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-                    }
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const bool hi = (lane & 8) != 0;
-                        const float keep = hi ? part[b + 2] : part[b], give = hi ? part[b] : part[b + 2];
-                        part[b] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
-                    }
-                    {
-                        const bool hi = (lane & 4) != 0;
-                        const float keep = hi ? part[1] : part[0], give = hi ? part[0] : part[1];
-                        part[0] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-                    }
-                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
-                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
-                    const int b_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    const int c = nt * 128 + 16 * b_mine + res;
-                    if (c < K) argmin_take(bd, bi, ref_distance(xx, part[0], __ldg(ee + c)), c);
-                }
+        ListWalk walk(mask, n_code_tiles);
+        while (walk.next()) {
+            const int nt0 = walk.nt, res0 = walk.res;
+            const bool two = walk.next();
+            const int nt1 = walk.nt, res1 = walk.res;
+            const int c0 = nt0 * 128 + 16 * b_mine + res0, c1 = nt1 * 128 + 16 * b_mine + res1;
+            const float e0 = c0 < K ? __ldg(ee + c0) : inf;
+            const float e1 = (two && c1 < K) ? __ldg(ee + c1) : inf;
+            float p0[8], p1[8];
+            list_dot8<VEC, MAXQ>(k, D, K, nt0, res0, lane, xr, p0);
+            if (two) list_dot8<VEC, MAXQ>(k, D, K, nt1, res1, lane, xr, p1);
+            const float d0 = list_reduce8(p0, lane);
+            if (c0 < K) argmin_take(bd, bi, ref_distance(xx, d0, e0), c0);
+            if (two) {
+                const float d1 = list_reduce8(p1, lane);
+                if (c1 < K) argmin_take(bd, bi, ref_distance(xx, d1, e1), c1);
             }
         }
         // combine the lanes (lanes sharing a code hold identical values)

@@ -394,7 +394,7 @@ struct __align__(16) Smem {           // control block placed after the data sta
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
     uint32_t issued[2];  // dual_issue: code-tile batches each MMA issuer has got past the accumulator-empty wait of (its own count)
-    alignas(16) float err_c[4];      // e_norm_max, e_err_max, 1.2e-7 Dp e_norm_max, 4 ulp(t): the per-frame FP16 error bound's constants (scan groups)
+    alignas(16) float err_c[4];      // [0], [1]: 2 err <= err_c[0] * ||x||^2 + err_c[1] (a-priori bound, linear in ||x||^2: no sqrt in the scan groups)
 };
 // after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
 // for their back stage); then either the folded -(||e||^2/2 - B) tiles or the FP32 offset vector.
@@ -429,10 +429,16 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ctl->issued[0] = ctl->issued[1] = 0u;
-        ctl->err_c[0] = e_norm_max;
-        ctl->err_c[1] = __uint_as_float(p.hdr->e_err_max_bits);
-        ctl->err_c[2] = 1.2e-7f * float(p.Dp) * e_norm_max;
-        ctl->err_c[3] = 4.f * ks.ulp;
+        {
+            // err = ||x - x16|| max||e16|| + ||x|| max||e - e16|| + acc_err + 4 ulp  <=  A ||x|| + B   with ||x - x16|| <= 2^-11 (1 + 2^-10) ||x||
+            // (+ the sub-normal floor), and ||x|| <= (||x||^2 / c + c) / 2 for any c > 0 (c = max||e16||, the typical frame norm)
+            const float A = 4.8876e-4f * e_norm_max + __uint_as_float(p.hdr->e_err_max_bits) + 1.2e-7f * float(p.Dp) * e_norm_max;
+            const float B = 4.f * ks.ulp + sqrtf(float(p.Dp)) * 3.0e-8f * e_norm_max;
+            const float c = fmaxf(e_norm_max, 1.0e-20f);
+            ctl->err_c[0] = 1.001f * A / c;                     // 2 err <= (A / c) ||x||^2 + (A c + 2 B)
+            ctl->err_c[1] = 1.001f * (A * c + 2.f * B);
+            ctl->err_c[2] = ctl->err_c[3] = 0.f;
+        }
     }
     // the folded offset must be representable as three FP16 terms; otherwise (absurdly large norms) every frame falls back
     const bool fold_ok = ks.offset < 3.0e4f;
@@ -1006,12 +1012,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             // whose maximum is.  (rowstat of this tile was written by the front group before the tile's MMAs were issued.)
             uint32_t chains = 1u << res;
             {
-                const float2 st = rowstat[cb * TM + r];
-                const float4 ec = *reinterpret_cast<const float4*>(ctl->err_c);
-                const float xn = sqrtf(st.x);
-                const float acc_err = ec.z * xn;
-                const float err = sqrtf(st.y) * ec.x + xn * ec.y + acc_err + ec.w;    // == finish()'s err
-                const float reach = __uint_as_float(r1) - 2.f * err;
+                // 2 err <= err_c[0] ||x||^2 + err_c[1]: an a-priori bound (looser than finish()'s measured err, so the flagged
+                // set is a superset of what the proof needs) that costs one FMA here instead of two square roots
+                const float reach = __uint_as_float(r1) - fmaf(ctl->err_c[0], rowstat[cb * TM + r].x, ctl->err_c[1]);
                 if (!(__uint_as_float(r2) < reach)) {
                     chains = 0u;
 #pragma unroll
@@ -1121,8 +1124,9 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
-    p.dual_issue = (p.resident && !p.pair && p.n_nt >= 2 && p.n_nt % 2 == 0) ? 1 : 0;   // (even: code-tile parity == batch parity)
-    if (tc_env().dual >= 0) p.dual_issue = p.dual_issue && tc_env().dual != 0;
+    p.dual_issue = 0;    // opt-in (VQ_K1_DUAL=1): measured equal to the single issuer (0.0752 vs 0.0754 ms), so off by default
+    const bool dual_possible = p.resident && !p.pair && p.n_nt >= 2 && p.n_nt % 2 == 0;   // (even: code-tile parity == batch parity)
+    if (tc_env().dual > 0 && dual_possible) p.dual_issue = 1;
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
     if (p.a_bufs < 1) return "emb_width > 512 (the FP16 A operand must fit the TMEM columns next to the accumulators)";

@@ -1,50 +1,33 @@
-// K2 forward + K3a in ONE pass over x (training forward, K <= 512, D <= 128, T % 4 == 0):
+// K2 forward + K3a in ONE pass over x (training forward, K <= 512, T % 4 == 0):
 //   x_q = (x + (e - x)) * mask, commit-loss / fit reductions        (bottleneck.py:143-145,194,197,118-124,201)
 //   per-code sums and counts of the valid frames                     (bottleneck.py:64-68)
-// The separate K3a kernel re-read x (152 MB at the bench shape) through 256-byte pieces at 0.24 of the HBM peak; here the
-// x tile is already in shared memory for the straight-through arithmetic, so the EMA statistics cost no HBM traffic at all.
+// The separate K3a kernel re-read x (152 MB at the bench shape) at 0.24 of the HBM peak; here the x tile is already in
+// shared memory for the straight-through arithmetic, so the EMA statistics cost no HBM traffic.
 //
-// Where the [K][D] FP32 accumulators live: shared memory is full (three pipeline stages of x + gathered codebook rows =
-// 209 KB), but the SM's 256 KB of TENSOR MEMORY are idle in this kernel and have exactly the right shape -- 128 lanes
-// (depth) x 512 columns (code) x 4 bytes.  Each 64-frame tile is sorted by code (one warp, bitonic, one tile ahead); a
-// run of equal codes is summed in registers (lane == depth) and added to its TMEM column with one tcgen05.ld / add /
-// tcgen05.st, so a hot code costs one update per tile, not one per frame, and no two warps ever touch the same column in
-// the same tile.  Warp w works on TMEM lane quadrant w % 4 (depths 32 (w % 4) ..+31) and takes every fourth run.  The
-// columns are flushed to the global statistics buffer with coalesced FP32 reductions when the CTA is done.
+// Work unit = 64 frames x 64 depths.  A CTA owns ONE 64-deep depth slice (blockIdx.y) and a private [K][64] FP32 slab of
+// per-code sums in shared memory (128 KB at K = 512) next to a three-stage ring of x tiles and a two-stage ring of gathered
+// codebook rows (87 KB); the CTAs of a slice stride over the frame tiles.  Each tile's frames are sorted by code (one warp,
+// bitonic, one tile ahead); a run of equal codes is summed in registers (lane == depth) by the warp in whose row range it
+// starts and added to the slab with ONE non-atomic read-modify-write, so a hot code costs one update per tile, not one per
+// frame, and no two warps touch the same slab row in the same tile.  The slab is flushed once per CTA with FP32 reductions.
+// (First version of this kernel kept the accumulators in tensor memory -- 128 lanes x 512 columns is exactly [D][K] -- but
+//  single-column tcgen05.ld / st cost ~100 cycles each whatever their size: 0.32 ms against 0.098 ms for K2 alone.)
 #pragma once
 #include "k2_gather.cuh"
 
 namespace vq {
 
 constexpr int FE_THREADS = 512;
-constexpr int FE_XS = G_TT + 4;                      // row stride of the x tile AND of the gathered rows (68 floats, 16-byte aligned rows;
+constexpr int FE_WARPS = FE_THREADS / 32;
+constexpr int FE_DS = 64;                            // depths per work unit (= slab width)
+constexpr int FE_XS = G_TT + 4;                      // row stride of the x tile and of the gathered rows (68 floats: 16-byte aligned rows,
                                                      // lane == depth reads of one frame are 4-way bank conflicts instead of 32-way)
-constexpr int FE_NST = 3;
-constexpr int FE_STAGE_FLOATS = 2 * GA_DS * FE_XS;   // x tile + codebook rows
-constexpr int FE_KMAX = 512, FE_DMAX = 128;
-constexpr size_t FE_SMEM = size_t(FE_NST) * FE_STAGE_FLOATS * 4 + GA_RING * G_TT * 12 + 2 * G_TT * 4 + FE_KMAX * 4;
-
-__device__ __forceinline__ void fe_tmem_ld1(uint32_t taddr, float& v) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    v = __uint_as_float(r);
-}
-__device__ __forceinline__ void fe_tmem_st1(uint32_t taddr, float v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
-}
-__device__ __forceinline__ void fe_tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void fe_tmem_zero16(uint32_t taddr) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+constexpr int FE_NX = 3, FE_NE = 2;                  // x stages (two tiles in flight), gathered-row stages
+constexpr int FE_TILE_FLOATS = FE_DS * FE_XS;        // 4352 floats = 17 KB
+constexpr int FE_KMAX = 512;
+constexpr int FE_PER = (G_TT + FE_WARPS - 2) / (FE_WARPS - 1);   // sorted rows per accumulating warp (5): warp 15 sorts
+inline size_t fe_smem_bytes(int K) {
+    return size_t(FE_NX + FE_NE) * FE_TILE_FLOATS * 4 + GA_RING * G_TT * 12 + 2 * G_TT * 4 + (size_t(K) * FE_DS + K) * 4;
 }
 
 __global__ void __launch_bounds__(FE_THREADS, 1)
@@ -53,44 +36,34 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
                       double* __restrict__ scalars, float* __restrict__ results, float* __restrict__ stats,
                       unsigned int total_blocks) {
     extern __shared__ __align__(16) float smem[];
-    int64_t* s_idx = reinterpret_cast<int64_t*>(smem + size_t(FE_NST) * FE_STAGE_FLOATS);   // [GA_RING][G_TT]
+    float* xs_base = smem;                                                                   // [FE_NX][FE_DS][FE_XS]
+    float* es_base = smem + FE_NX * FE_TILE_FLOATS;                                          // [FE_NE][FE_DS][FE_XS]
+    int64_t* s_idx = reinterpret_cast<int64_t*>(es_base + FE_NE * FE_TILE_FLOATS);           // [GA_RING][G_TT]
     float* s_mask = reinterpret_cast<float*>(s_idx + GA_RING * G_TT);                        // [GA_RING][G_TT]
     uint32_t* sorted = reinterpret_cast<uint32_t*>(s_mask + GA_RING * G_TT);                 // [2][G_TT]  (code << 8 | frame), ~0u = no row
-    float* s_cnt = reinterpret_cast<float*>(sorted + 2 * G_TT);                              // [FE_KMAX]
+    float* slab = reinterpret_cast<float*>(sorted + 2 * G_TT);                               // [K][FE_DS]
+    float* s_cnt = slab + size_t(K) * FE_DS;                                                 // [K]  (slice 0 only)
     __shared__ double red[32];
     __shared__ bool is_last;
-    __shared__ int4 s_loc[GA_RING];
-    __shared__ uint32_t s_tmem;
+    __shared__ int2 s_loc[GA_RING];           // (utterance, first frame) of the units in the ring; x < 0: none
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_per_utt = (T + G_TT - 1) / G_TT;
     const int n_units = N * tiles_per_utt;
     const int u0 = blockIdx.x, step = gridDim.x;
-    const int dn = D;                                              // one depth slice: D <= 128
+    const int d0 = blockIdx.y * FE_DS, dn = min(FE_DS, D - d0);
+    const bool first_slice = blockIdx.y == 0;                      // the scalar reductions and the counts are done once, by slice 0
 
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(&s_tmem))), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    for (int c = tid; c < FE_KMAX; c += FE_THREADS) s_cnt[c] = 0.f;
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    const int quad = warp & 3, sub = warp >> 2;                    // TMEM lane quadrant of this warp; which runs / columns it takes
-    const uint32_t tq = tmem + (uint32_t(quad * 32) << 16);
-#pragma unroll
-    for (int c0 = 0; c0 < 128; c0 += 16) fe_tmem_zero16(tq + uint32_t(128 * sub + c0));
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    for (int i = tid; i < K * FE_DS + K; i += FE_THREADS) slab[i] = 0.f;
 
     auto prefetch_im = [&](int j, int u) {
         if (tid < G_TT) {
             const int slot = j & (GA_RING - 1);
-            int4 loc = make_int4(0, 0, 0, 0);
+            int2 loc = make_int2(-1, 0);
             bool copied = false;
             if (u < n_units) {
                 const int n = u / tiles_per_utt, t0 = (u - n * tiles_per_utt) * G_TT;
-                loc = make_int4(n, t0, 0, 1);
+                loc = make_int2(n, t0);
                 const int t = t0 + tid;
                 if (t < T) {
                     cp_async8(s_idx + slot * G_TT + tid, idx + int64_t(n) * T + t);
@@ -103,42 +76,43 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
             if (tid == 0) s_loc[slot] = loc;
         }
     };
-    auto issue = [&](int st, int ring) {
-        const int4 loc = s_loc[ring];
-        if (loc.w) {
-            const int n = loc.x, t0 = loc.y;
-            float* S = smem + size_t(st) * FE_STAGE_FLOATS;
+    auto issue = [&](int st, int ring) {                           // x tile of the unit in ring slot `ring` -> x stage st
+        const int2 loc = s_loc[ring];
+        if (loc.x >= 0) {
+            float* S = xs_base + size_t(st) * FE_TILE_FLOATS;
 #pragma unroll
-            for (int r = 0; r < GA_DS * (G_TT / 4) / FE_THREADS; ++r) {
+            for (int r = 0; r < FE_DS * (G_TT / 4) / FE_THREADS; ++r) {
                 const int i = tid + r * FE_THREADS, d = i >> 4, c4 = (i & 15) * 4;
-                if (d < dn && t0 + c4 < T) cp_async16(S + d * FE_XS + c4, x + (int64_t(n) * D + d) * T + t0 + c4);
+                if (d < dn && loc.y + c4 < T) cp_async16(S + d * FE_XS + c4, x + (int64_t(loc.x) * D + d0 + d) * T + loc.y + c4);
             }
         }
         cp_async_commit();
     };
+    // codebook rows of a unit through registers: warp w takes frames 4w .. 4w+3 and all depth blocks of 8 (lane = 4 * depth + row,
+    // so the transposing stores hit 32 different banks); loads are issued one iteration before the stores
     const int g_r = 4 * warp + (lane & 3), g_dd = lane >> 2;
-    auto gather_ld = [&](int ring, float (&ev)[GA_DS / 8]) {
-        const int4 loc = s_loc[ring];
-        if (loc.w) {
+    auto gather_ld = [&](int ring, float (&ev)[FE_DS / 8]) {
+        if (s_loc[ring].x >= 0) {
             const int code = int(min(max(s_idx[ring * G_TT + g_r], int64_t(0)), int64_t(K - 1)));
-            const float* src = k + size_t(code) * D + g_dd;
+            const float* src = k + size_t(code) * D + d0 + g_dd;
 #pragma unroll
-            for (int db = 0; db < GA_DS / 8; ++db) ev[db] = (8 * db + g_dd < dn) ? __ldg(src + 8 * db) : 0.f;
+            for (int db = 0; db < FE_DS / 8; ++db) ev[db] = (8 * db + g_dd < dn) ? __ldg(src + 8 * db) : 0.f;
         }
     };
-    auto gather_st = [&](int st, const float (&ev)[GA_DS / 8]) {
-        float* dst = smem + size_t(st) * FE_STAGE_FLOATS + GA_DS * FE_XS + g_dd * FE_XS + g_r;
+    auto gather_st = [&](int st, const float (&ev)[FE_DS / 8]) {
+        float* dst = es_base + size_t(st) * FE_TILE_FLOATS + g_dd * FE_XS + g_r;
 #pragma unroll
-        for (int db = 0; db < GA_DS / 8; ++db) dst[8 * db * FE_XS] = ev[db];
+        for (int db = 0; db < FE_DS / 8; ++db) dst[8 * db * FE_XS] = ev[db];
     };
     // keys of the unit in ring slot `ring`: (code << 8) | frame for valid frames, ~0u otherwise; bitonic sort in one warp
     auto sort_unit = [&](int ring, uint32_t* dst) {
         uint32_t key[2];
+        const bool exists = s_loc[ring].x >= 0;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int t = r * 32 + lane;
             const int64_t ci = s_idx[ring * G_TT + t];
-            key[r] = (s_mask[ring * G_TT + t] != 0.f && ci >= 0 && s_loc[ring].w) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
+            key[r] = (exists && s_mask[ring * G_TT + t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int kk = 2; kk <= G_TT; kk <<= 1) {
@@ -169,43 +143,41 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
     for (int j = 0; j < GA_AHEAD; ++j) prefetch_im(j, u0 + j * step);
     cp_async_commit();
     cp_async_wait<0>();
-    __syncthreads();
-    float ev[GA_DS / 8];
+    __syncthreads();                                               // (also: the slab is zeroed)
+    float ev[FE_DS / 8];
 #pragma unroll
-    for (int j = 0; j < GA_DS / 8; ++j) ev[j] = 0.f;
+    for (int j = 0; j < FE_DS / 8; ++j) ev[j] = 0.f;
     gather_ld(0, ev);
     gather_st(0, ev);
-    if (warp == 15) sort_unit(0, sorted);
+    if (warp == FE_WARPS - 1) sort_unit(0, sorted);
 #pragma unroll
-    for (int j = 0; j < FE_NST - 1; ++j) issue(j, j);
+    for (int j = 0; j < FE_NX - 1; ++j) issue(j, j);
 
     int it = 0;
     for (int u = u0; u < n_units; u += step, ++it) {
-        gather_ld((it + 1) & (GA_RING - 1), ev);
-        prefetch_im(it + GA_AHEAD, u + GA_AHEAD * step);
-        cp_async_wait<FE_NST - 2>();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                          // x of unit u landed; sorted[it & 1] complete; last unit's TMEM updates done
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue((it + FE_NST - 1) % FE_NST, (it + FE_NST - 1) & (GA_RING - 1));
+        gather_ld((it + 1) & (GA_RING - 1), ev);                   // stored at the end of this iteration
+        prefetch_im(it + GA_AHEAD, u + GA_AHEAD * step);           // joins the copy group committed by issue() below
+        cp_async_wait<FE_NX - 2>();                                // this thread's copies of unit u have landed
+        __syncthreads();                                           // ... everyone's; sorted[it & 1] and Es[it & 1] complete; stage of unit u-1 free
+        issue((it + FE_NX - 1) % FE_NX, (it + FE_NX - 1) & (GA_RING - 1));
 
-        const int4 cur = s_loc[it & (GA_RING - 1)];
+        const int2 cur = s_loc[it & (GA_RING - 1)];
         const int n = cur.x, t0 = cur.y;
         const int tt = min(G_TT, T - t0);
-        const float* S = smem + size_t(it % FE_NST) * FE_STAGE_FLOATS;
-        const float* Es = S + GA_DS * FE_XS;
+        const float* S = xs_base + size_t(it % FE_NX) * FE_TILE_FLOATS;
+        const float* Es = es_base + size_t(it % FE_NE) * FE_TILE_FLOATS;
         const float* sm = s_mask + (it & (GA_RING - 1)) * G_TT;
         // ---- straight-through output + loss reductions (bottleneck.py:194-201)
         {
             const int t4 = (tid & 15) * 4, dg = tid >> 4;
-            if (tid < G_TT) msum_local += double(sm[tid]);
+            if (first_slice && tid < G_TT) msum_local += double(sm[tid]);
             if (t4 < tt) {
                 const float4 m4 = *reinterpret_cast<const float4*>(sm + t4);
                 const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
                 const float vv[4] = {m4.x != 0.f ? 1.f : 0.f, m4.y != 0.f ? 1.f : 0.f, m4.z != 0.f ? 1.f : 0.f, m4.w != 0.f ? 1.f : 0.f};
                 float accf[4] = {0.f, 0.f, 0.f, 0.f};
-                float* dst = out + (int64_t(n) * D) * T + t0 + t4;
-#pragma unroll 4
+                float* dst = out + (int64_t(n) * D + d0) * T + t0 + t4;
+#pragma unroll
                 for (int d = dg; d < dn; d += FE_THREADS / 16) {
                     const float4 e4 = *reinterpret_cast<const float4*>(Es + d * FE_XS + t4);
                     const float4 x4 = *reinterpret_cast<const float4*>(S + d * FE_XS + t4);
@@ -224,78 +196,50 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
                 sq += double((accf[0] * vv[0] + accf[1] * vv[1]) + (accf[2] * vv[2] + accf[3] * vv[3]));
             }
         }
-        // ---- EMA statistics of this unit (bottleneck.py:64-68): runs of equal codes -> one TMEM column update each
-        if (warp == 15) sort_unit((it + 1) & (GA_RING - 1), sorted + ((it + 1) & 1) * G_TT);   // next unit's keys (its indices landed a wait ago)
-        if (quad * 32 < dn) {
-            // Runs are found lane-parallel (two ballots over the sorted keys give a 64-bit mask of run heads) and this warp
-            // takes runs sub, sub + 4, ...: at most 16.  Their sums stay in registers; the 16 TMEM columns are then read,
-            // updated and written back as ONE batch, so the tensor-memory round trip is paid once per tile, not per run.
+        // ---- EMA statistics of this unit (bottleneck.py:64-68): runs of equal codes -> one slab update each
+        if (warp == FE_WARPS - 1) {
+            sort_unit((it + 1) & (GA_RING - 1), sorted + ((it + 1) & 1) * G_TT);   // next unit's keys (its indices landed a wait ago)
+        } else {
             const uint32_t* keys = sorted + (it & 1) * G_TT;
-            const float* col = S + (quad * 32 + lane) * FE_XS;        // this lane's depth row of the x tile
-            const uint32_t k0 = keys[lane], k1 = keys[32 + lane];
-            const bool v0 = k0 != 0xFFFFFFFFu, v1 = k1 != 0xFFFFFFFFu;
-            const uint32_t p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
-            const uint32_t k0_last = __shfl_sync(0xffffffffu, k0, 31);
-            const bool h0 = v0 && (lane == 0 || (k0 >> 8) != (p0 >> 8));
-            const bool h1 = v1 && ((k1 >> 8) != ((lane == 0 ? k0_last : p1) >> 8));
-            unsigned long long heads = (unsigned long long)__ballot_sync(0xffffffffu, h0) |
-                                       ((unsigned long long)__ballot_sync(0xffffffffu, h1) << 32);
-            const int nvalid = __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, v1));
-            for (int sk = 0; sk < sub; ++sk) heads &= heads - 1;      // runs 0 .. sub-1 belong to the other warps of this quadrant
-            float a[16];
-            uint32_t cc[16];
-            int len[16];
-            int nr = 0;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                a[r] = 0.f; cc[r] = 0u; len[r] = 0;
-                if (heads) {                                          // (warp-uniform)
-                    const int sb = __ffsll((long long)heads) - 1;
-                    heads &= heads - 1;
-                    const int eb = heads ? __ffsll((long long)heads) - 1 : nvalid;
-                    heads &= heads - 1; heads &= heads - 1; heads &= heads - 1;      // the next three runs are other warps'
-                    const uint32_t ks = sb < 32 ? __shfl_sync(0xffffffffu, k0, sb) : __shfl_sync(0xffffffffu, k1, sb - 32);
-                    float acc = 0.f;
-                    for (int f = sb; f < eb; ++f) {
-                        const uint32_t kf = f < 32 ? __shfl_sync(0xffffffffu, k0, f) : __shfl_sync(0xffffffffu, k1, f - 32);
-                        acc += col[kf & 255u];
-                    }
-                    a[r] = acc; cc[r] = ks >> 8; len[r] = eb - sb; nr = r + 1;
-                }
+            const int lo = warp * FE_PER, hi = min(G_TT, lo + FE_PER);
+            int i = lo;
+            const uint32_t kprev = (lo > 0 && lo < G_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
+            // skip the tail of a run that started in an earlier warp's range
+            while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
+            while (i < hi) {
+                uint32_t key = keys[i];
+                if (key == 0xFFFFFFFFu) break;                                    // sorted: no more valid frames
+                const uint32_t code = key >> 8;
+                float a0 = 0.f, a1 = 0.f, cnt = 0.f;
+                do {                                                              // one run; may continue past hi
+                    const float* col = S + (key & 255u);
+                    if (lane < dn) a0 += col[lane * FE_XS];
+                    if (lane + 32 < dn) a1 += col[(lane + 32) * FE_XS];
+                    cnt += 1.f;
+                    ++i;
+                    key = i < G_TT ? keys[i] : 0xFFFFFFFFu;
+                } while (key != 0xFFFFFFFFu && (key >> 8) == code);
+                slab[size_t(code) * FE_DS + lane] += a0;
+                slab[size_t(code) * FE_DS + lane + 32] += a1;
+                if (first_slice && lane == 0) s_cnt[code] += cnt;
             }
-            uint32_t v[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-                if (r < nr) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[r]) : "r"(tq + cc[r]) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-                if (r < nr) {
-                    fe_tmem_st1(tq + cc[r], __uint_as_float(v[r]) + a[r]);
-                    if (quad == 0 && lane == 0) s_cnt[cc[r]] += float(len[r]);
-                }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        gather_st((it + 1) % FE_NST, ev);
+        gather_st((it + 1) % FE_NE, ev);                           // Es[(it+1) & 1] was last read in iteration it-1
     }
     cp_async_wait<0>();
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- flush the TMEM accumulators: lane == depth, so each reduction is a coalesced 128-byte segment of one code row
+    // ---- flush the slab: one FP32 reduction per touched (code, depth)
     {
         float* sums = stats;
         float* counts = stats + size_t(K) * D;
-        const int d = quad * 32 + lane;
-        for (int c0 = 128 * sub; c0 < 128 * sub + 128 && c0 < K; c0 += 16) {
-            float v[16];
-            fe_tmem_ld16(tq + uint32_t(c0), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < K && d < dn && v[i] != 0.f) atomicAdd(&sums[size_t(c0 + i) * D + d], v[i]);
+        for (int i = tid; i < K * FE_DS; i += FE_THREADS) {
+            const int c = i / FE_DS, d = i % FE_DS;
+            const float v = slab[i];
+            if (d < dn && v != 0.f) atomicAdd(&sums[size_t(c) * D + d0 + d], v);
         }
-        for (int c = tid; c < K; c += FE_THREADS)
-            if (s_cnt[c] != 0.f) atomicAdd(&counts[c], s_cnt[c]);
+        if (first_slice)
+            for (int c = tid; c < K; c += FE_THREADS)
+                if (s_cnt[c] != 0.f) atomicAdd(&counts[c], s_cnt[c]);
     }
     {
         double s1 = block_sum(sq, red);
@@ -304,7 +248,7 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
         if (tid == 0) {
             atomicAdd(&scalars[VQ_S_SUM_MIN_D], s3);
             atomicAdd(&scalars[VQ_S_COMMIT_SQ], s1);
-            atomicAdd(&scalars[VQ_S_MASK_SUM], s2);
+            if (first_slice) atomicAdd(&scalars[VQ_S_MASK_SUM], s2);
             __threadfence();
             unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(&scalars[VQ_S_TICKET]), 1u);
             is_last = (ticket == total_blocks - 1);
@@ -317,12 +261,6 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
             results[VQ_R_FIT] = float(sc[VQ_S_SUM_MIN_D] / double(K));
             *reinterpret_cast<unsigned int*>(&scalars[VQ_S_TICKET]) = 0u;
         }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
 }
 

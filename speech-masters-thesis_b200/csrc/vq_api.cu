@@ -184,7 +184,7 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         // Programmatic dependent launch: the kernel is set up while the main kernel still runs (which signals
         // launch_dependents right after its prologue) and waits on griddepcontrol.wait before it reads the count, so the
         // usual empty-worklist case costs ~3 us less than a serialised launch.
-        const int gx = int(std::min<int64_t>(4 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
+        const int gx = int(std::min<int64_t>(16 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx);
         cfg.blockDim = dim3(L_WARPS * 32);
@@ -196,13 +196,14 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         cfg.numAttrs = (g_prof.on && pslot >= 0) ? 0 : 1;          // (event records between the two kernels serialise them anyway)
         const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
         const int n_code_tiles = w.Kp / 128;
-        if (vec) {
-            VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_list_kernel<true>, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d,
-                                          scalars, (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr));
-        } else {
-            VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_list_kernel<false>, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d,
-                                          scalars, (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr));
-        }
+        auto launch_list = [&](auto kernel) {
+            return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d, scalars,
+                                      (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr);
+        };
+        if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1>));
+        else if (vec) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 4>));
+        else if (D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<false, 1>));
+        else VQ_CUDA_OK(launch_list(assign_list_kernel<false, 4>));
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));
@@ -240,7 +241,8 @@ int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, cons
 }
 
 int vq_gather_st_fwd_ema_supported(int64_t D, int64_t T, int K) {
-    return (K > 0 && K <= FE_KMAX && D > 0 && D <= FE_DMAX && T > 0 && T % 4 == 0 && T < (int64_t(1) << 31)) ? 1 : 0;
+    return (K > 0 && K <= FE_KMAX && D > 0 && D <= 512 && T > 0 && T % 4 == 0 && T < (int64_t(1) << 31) &&
+            fe_smem_bytes(K) <= size_t(227 * 1024) - 2048) ? 1 : 0;
 }
 
 int vq_gather_st_fwd_ema(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,
@@ -250,14 +252,15 @@ int vq_gather_st_fwd_ema(const float* x, const int64_t* idx, const float* mask, 
     if (N * T == 0) return 0;
     VQ_REQUIRE(x && idx && k && x_q, "null pointer");
     VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
-    VQ_REQUIRE(vq_gather_st_fwd_ema_supported(D, T, K), "fused forward + EMA needs K <= 512, D <= 128, T % 4 == 0");
+    VQ_REQUIRE(vq_gather_st_fwd_ema_supported(D, T, K), "fused forward + EMA needs K <= 512, D <= 512, T % 4 == 0");
     VQ_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_q) & 15) == 0, "x / x_q must be 16-byte aligned");
     const int64_t units = N * ((T + G_TT - 1) / G_TT);
     VQ_REQUIRE(units < (int64_t(1) << 31), "too many tiles");
-    VQ_CUDA_OK(ensure_dynamic_smem(gather_fwd_ema_kernel, int(FE_SMEM)));
-    const int grid = int(std::min<int64_t>(units, num_sms()));
-    gather_fwd_ema_kernel<<<grid, FE_THREADS, FE_SMEM, static_cast<cudaStream_t>(stream)>>>(x, idx, mask, k, int(N), int(D), int(T), K, x_q,
-                                                                                          scalars, results, stats, (unsigned int)grid);
+    VQ_CUDA_OK(ensure_dynamic_smem(gather_fwd_ema_kernel, int(227 * 1024 - 2048)));
+    const int slices = int((D + FE_DS - 1) / FE_DS);
+    const int gx = int(std::min<int64_t>(units, std::max(1, num_sms() / slices)));
+    gather_fwd_ema_kernel<<<dim3(gx, slices), FE_THREADS, fe_smem_bytes(K), static_cast<cudaStream_t>(stream)>>>(
+        x, idx, mask, k, int(N), int(D), int(T), K, x_q, scalars, results, stats, (unsigned int)(gx * slices));
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

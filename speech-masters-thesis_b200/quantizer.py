@@ -171,7 +171,7 @@ class _QuantizeST(torch.autograd.Function):
             after_assign(idx)
         x_q = torch.empty_like(x)
         if n * t and fused_stats is not None:
-            # K2 and K3a in one pass over x (EMA accumulators in tensor memory): K1 -> K2+K3a -> all-reduce -> K3b
+            # K2 and K3a in one pass over x: K1 -> K2+K3a -> all-reduce -> K3b
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_fwd_ema(ptr(x), ptr(idx), ptr(mask), ptr(k), n, d, t, kk, ptr(x_q), ptr(scalars),
                                                ptr(results), ptr(fused_stats), _stream(x)), "vq_gather_st_fwd_ema")
@@ -292,7 +292,7 @@ class BottleneckBlock(nn.Module):
 
     # ---- EMA (bottleneck.py:60-90)
     def _fuse_ema_ok(self, x):
-        """K2 + K3a in one kernel (EMA accumulators in tensor memory) when the shape allows it; ``fuse_ema`` = False keeps
+        """K2 + K3a in one kernel (one pass over x, per-code sums in a shared-memory slab) when the shape allows it; ``fuse_ema`` = False keeps
         them apart (K3a before K2, so the all-reduce overlaps K2), None = fuse whenever possible."""
         if self.fuse_ema is False or x.numel() == 0 or x.data_ptr() % 16:
             return False

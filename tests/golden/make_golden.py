@@ -124,8 +124,65 @@ def case_encode_decode(name, seed, n, d, t, lengths, k_bins):
     print(name, "rows", n * t)
 
 
+def grouped_inputs(seed, b, c, tx, ty, n_vocab, l_bins, x_lens, y_lens):
+    """Inputs of the phoneme-conditioned quantiser (models/vqtts/bottleneck.py:19): latents y_enc [b, c, ty], token ids
+    x_id [b, tx] and a hard monotonic alignment attn [b, tx, ty] (frame j of utterance i belongs to exactly one token; padded
+    frames / tokens have all-zero columns / rows)."""
+    g = torch.Generator().manual_seed(seed)
+    code = torch.randn(n_vocab * l_bins, c, generator=g)
+    x_id = torch.randint(0, n_vocab, (b, tx), generator=g)
+    attn = torch.zeros(b, tx, ty)
+    for i in range(b):
+        cuts = torch.sort(torch.randperm(y_lens[i] - 1, generator=g)[:x_lens[i] - 1] + 1).values.tolist()
+        bounds = [0] + cuts + [y_lens[i]]
+        for j in range(x_lens[i]):
+            attn[i, j, bounds[j]:bounds[j + 1]] = 1.0
+        x_id[i, x_lens[i]:] = 0
+    tok = torch.matmul(x_id.float().unsqueeze(1), attn).squeeze(1).long()            # [b, ty] token of every frame
+    rel = torch.randint(0, l_bins, (b, ty), generator=g)
+    y_enc = code[tok * l_bins + rel].permute(0, 2, 1).contiguous() + 0.4 * torch.randn(b, c, ty, generator=g)
+    return y_enc, x_id, attn, code
+
+
+def case_grouped(name, seed, b, c, tx, ty, n_vocab, l_bins, x_lens, y_lens, training=True, thr=1.0, elem_scale=4.0, rng_seed=4321):
+    from models.vqtts.bottleneck import Bottleneck as GroupedBottleneck          # the reference
+    y_enc, x_id, attn, code = grouped_inputs(seed, b, c, tx, ty, n_vocab, l_bins, x_lens, y_lens)
+    blk = GroupedBottleneck(n_vocab, l_bins, c, 0.99, thr)
+    blk.k = code.clone()
+    blk.init = True
+    blk.k_sum = code.clone() * elem_scale
+    blk.k_elem = torch.ones(n_vocab * l_bins) * elem_scale
+    blk.train(training)
+    before = dict(k0=np_(blk.k), k_sum0=np_(blk.k_sum), k_elem0=np_(blk.k_elem))
+    yg = y_enc.clone().requires_grad_(True)
+    torch.manual_seed(rng_seed)
+    q_rel, y_d, commit, metrics = blk(yg, x_id, attn, update_k=training)
+    gw = torch.Generator().manual_seed(seed + 99)
+    w = torch.randn(y_d.shape, generator=gw)
+    ((w * y_d).sum() + 0.7 * commit).backward()
+    out = dict(y_enc=np_(y_enc), x_id=np_(x_id), attn=np_(attn), **before, q_rel=np_(q_rel), y_d=np_(y_d.contiguous()),
+               commit=np_(commit), grad_w=np_(w), grad_commit=np.float32(0.7), grad_y=np_(yg.grad),
+               k1=np_(blk.k), k_sum1=np_(blk.k_sum), k_elem1=np_(blk.k_elem), n_vocab=np.int32(n_vocab), l_bins=np.int32(l_bins),
+               mu=np.float32(0.99), threshold=np.float32(thr), training=np.int32(training), rng_seed=np.int64(rng_seed))
+    for key, val in metrics.items():
+        out["metric_" + key] = np_(val)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "frames", b * ty, "metrics", {k: float(v) for k, v in metrics.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)          # fixed summation order for the generator run
+    if "--grouped" in sys.argv:       # only the phoneme-conditioned quantiser cases (added in round 2)
+        # (b = 1 only: the reference's `torch.matmul(x_id, attn)` (vqtts/bottleneck.py:28) broadcasts a [b, tx] id matrix against
+        #  the [b, tx, ty] alignment into [b, b, ty] and fails to reshape for b > 1; the authors train it with batch size 1,
+        #  scripts/train_vqvae.sh:14)
+        case_grouped("grouped_v11_l32_d16", seed=21, b=1, c=16, tx=9, ty=60, n_vocab=11, l_bins=32, x_lens=[9], y_lens=[60])
+        case_grouped("grouped_padded_v4_l64_d128", seed=24, b=1, c=128, tx=12, ty=96, n_vocab=4, l_bins=64, x_lens=[10], y_lens=[77])
+        case_grouped("grouped_eval_v7_l64_d32", seed=22, b=1, c=32, tx=7, ty=48, n_vocab=7, l_bins=64, x_lens=[7], y_lens=[48],
+                     training=False)
+        case_grouped("grouped_revival_v5_l16_d8", seed=23, b=1, c=8, tx=6, ty=40, n_vocab=5, l_bins=16, x_lens=[5], y_lens=[33],
+                     thr=2.0, elem_scale=1.0)
+        sys.exit(0)
     # default width, ragged lengths, training step with EMA
     case_forward("train_k512_d128", seed=1, n=3, d=128, t=100, lengths=[100, 64, 37], k_bins=512, elem_scale=1.0)
     # clustered data, well-used codes (k_elem scaled so nothing is revived)

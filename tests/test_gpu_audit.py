@@ -123,10 +123,10 @@ def test_two_streams_do_not_share_a_workspace(vq):
         audit(xs[i], code, outs[i])
 
 
-@pytest.mark.parametrize("shape", [(64, 128, 512, True), (5, 96, 300, False), (3, 32, 40, True), (2, 128, 512, False)],
+@pytest.mark.parametrize("shape", [(64, 128, 512, True), (5, 96, 300, False), (3, 32, 40, True), (2, 128, 512, False), (3, 200, 96, True)],
                          ids=lambda s: f"N{s[0]}_D{s[1]}_K{s[2]}")
 def test_fused_forward_ema_matches_separate_kernels(vq, shape):
-    """vq_gather_st_fwd_ema (K2 + K3a in one pass, per-code accumulators in tensor memory) against the two separate kernels
+    """vq_gather_st_fwd_ema (K2 + K3a in one pass over x, per-code sums in a shared-memory slab) against the two separate kernels
     and against the oracle's one-hot GEMM statistics: x_q bit-equal, counts exact, sums 1e-5."""
     n, D, K, clustered = shape
     gen = torch.Generator().manual_seed(n * 1000 + D)
@@ -168,7 +168,7 @@ def test_fused_forward_ema_matches_separate_kernels(vq, shape):
     assert torch.allclose(stats[:K * D].view(K, D).cpu(), s_sum, rtol=1e-5, atol=2e-5)
     assert torch.equal(x_q.cpu(), a[1])
     # shapes the fused kernel does not take are refused, not mangled
-    assert lib.vq_gather_st_fwd_ema_supported(128, 1024, 513) == 0 and lib.vq_gather_st_fwd_ema_supported(129, 1024, 512) == 0
+    assert lib.vq_gather_st_fwd_ema_supported(128, 1024, 513) == 0 and lib.vq_gather_st_fwd_ema_supported(513, 1024, 512) == 0
     assert lib.vq_gather_st_fwd_ema_supported(128, 1023, 512) == 0 and lib.vq_gather_st_fwd_ema_supported(128, 1024, 512) == 1
 
 

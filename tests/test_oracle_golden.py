@@ -139,3 +139,31 @@ def test_synthetic_lengths_look_like_ljspeech():
     x, mask = O.synthetic_batch(lens[:3], 8, gen)
     assert x.shape == (3, 8, int(lens[:3].max())) and mask.shape == (3, 1, x.shape[2])
     assert torch.all(x[0, :, int(lens[0]):] == 0.25)
+
+
+GROUPED_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "grouped_*.npz")))
+
+
+@pytest.mark.parametrize("name", GROUPED_CASES)
+def test_grouped_forward_matches_reference(name):
+    """models/vqtts/bottleneck.py (phoneme-conditioned quantiser) restated in oracle.grouped_forward."""
+    torch.set_num_threads(1)
+    g = load(name)
+    st = state_from(g)
+    y = T(g["y_enc"]).clone().requires_grad_(True)
+    training = bool(g["training"])
+    torch.manual_seed(int(g["rng_seed"]))
+    q_rel, y_d, commit, metrics = O.grouped_forward(st, y, T(g["x_id"]), T(g["attn"]), int(g["n_vocab"]), int(g["l_bins"]),
+                                                    training=training, update_k=training)
+    assert q_rel.dtype == torch.int64 and np.array_equal(q_rel.numpy(), g["q_rel"])
+    assert np.array_equal(y_d.detach().contiguous().numpy(), g["y_d"])
+    close(commit.item(), g["commit"])
+    ((T(g["grad_w"]) * y_d).sum() + float(g["grad_commit"]) * commit).backward()
+    close(y.grad.numpy(), g["grad_y"], rtol=1e-6, atol=1e-8)
+    assert set(metrics) == {k[7:] for k in g if k.startswith("metric_")}
+    for key, val in metrics.items():
+        close(float(val), g["metric_" + key], rtol=1e-6, atol=1e-7)
+    if training:
+        close(st.k.numpy(), g["k1"], rtol=1e-6, atol=1e-7)
+        close(st.k_sum.numpy(), g["k_sum1"], rtol=1e-6, atol=1e-7)
+        close(st.k_elem.numpy(), g["k_elem1"], rtol=1e-6, atol=1e-7)
