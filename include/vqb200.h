@@ -89,6 +89,18 @@ int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames
               int64_t* idx, float* min_d, double* scalars,
               void* workspace, size_t workspace_bytes, int algo, void* stream);
 
+/* Grouped (phoneme-conditioned) K1 -- replaces the per-frame codebook gather + bmm + min of the TTS quantiser
+ * (models/vqtts/bottleneck.py:38-58): the codebook k is [n_vocab * l_bins, D]; frame j only competes among the l_bins
+ * codes of its token tok[j] (int64 [N*T], the aligned token ids of :28; values are clamped to [0, n_vocab)).
+ *   q_rel [N*T] int64: index inside the group (what the reference returns, :52);  q_abs = tok * l_bins + q_rel (:58), the
+ *   index dequantize / update_k use with the other entry points;  min_d [N*T] or NULL;  scalars[VQ_S_SUM_MIN_D] += sum(min_d).
+ * Exact FP32 on the CUDA cores (one warp per frame walks its token's code rows in place); same workspace as vq_assign,
+ * sized by vq_workspace_bytes(N, T, n_vocab * l_bins, D). */
+int vq_assign_grouped(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+                      const float* k, int n_vocab, int l_bins, const int64_t* tok,
+                      int64_t* q_rel, int64_t* q_abs, float* min_d, double* scalars,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Audit variant of vq_assign (tcgen05 path only): additionally writes, per frame, the four floats
  * {approximate best score, bound on every other code's approximate score, exact FP32 score of the shortlisted
  * code, rigorous FP16 error bound} into shortlist4 [N*T*4] (16-byte aligned), so tests can check that the

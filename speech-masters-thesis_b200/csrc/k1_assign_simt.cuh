@@ -313,4 +313,89 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grouped (phoneme-conditioned) assignment, models/vqtts/bottleneck.py:38-58: frame j only competes among the l_bins codes
+// of its aligned token tok[j]; K = n_vocab * l_bins (76 288 in the reference's TTS config).  The reference gathers a
+// [frames, l_bins, D] copy of the codebook (frames * l_bins * D * 4 bytes!) and runs a bmm; here one warp per frame walks
+// its token's code rows in place (they stay in L2), FP32, lowest index on ties.  Writes the relative index (what the
+// reference returns), the absolute index (what dequantize / update_k use, :58) and optionally the winning distance.
+template <bool VEC, int MAXQ>
+__global__ void __launch_bounds__(L_WARPS * 32)
+assign_grouped_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
+                      const float* __restrict__ ee, int n_vocab, int l_bins, const int64_t* __restrict__ tok,
+                      int64_t* __restrict__ q_rel, int64_t* __restrict__ q_abs, float* __restrict__ min_d,
+                      double* __restrict__ scalars) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const float inf = __int_as_float(0x7f800000);
+    const int64_t rows = N * T;
+    double sum = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * L_WARPS + warp; row < rows; row += int64_t(gridDim.x) * L_WARPS) {
+        const int64_t g = min(max(tok[row], int64_t(0)), int64_t(n_vocab - 1));
+        const float* src = x + (row / T) * int64_t(D) * T + (row % T);
+        const float* kg = k + size_t(g) * l_bins * D;
+        const float* eg = ee + size_t(g) * l_bins;
+        float xr[4 * MAXQ];
+        float xx = 0.f;
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = VEC ? 4 * (lane + 32 * q) + u : lane + 32 * (4 * q + u);
+                const float v = d < D ? __ldg(src + int64_t(d) * T) : 0.f;
+                xr[4 * q + u] = v;
+                xx = fmaf(v, v, xx);
+            }
+        xx = warp_sum(xx);
+        float bd = inf;
+        int bi = 0x7fffffff;
+        for (int c0 = 0; c0 < l_bins; c0 += 16) {                 // two segments of eight consecutive codes per step
+            const int ca = c0 + b_mine, cb = c0 + 8 + b_mine;
+            const float ea = ca < l_bins ? __ldg(eg + ca) : inf, eb = cb < l_bins ? __ldg(eg + cb) : inf;
+            float pa[8], pb[8];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const int c = c0 + b;
+                float acc = 0.f;
+                if (c < l_bins) {
+                    const float* er = kg + size_t(c) * D;
+                    if (VEC) {
+#pragma unroll
+                        for (int q = 0; q < MAXQ; ++q)
+                            if (4 * (lane + 32 * q) < D) {
+                                const float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + lane + 32 * q);
+                                acc = fmaf(xr[4 * q + 0], e4.x, acc); acc = fmaf(xr[4 * q + 1], e4.y, acc);
+                                acc = fmaf(xr[4 * q + 2], e4.z, acc); acc = fmaf(xr[4 * q + 3], e4.w, acc);
+                            }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4 * MAXQ; ++i)
+                            if (lane + 32 * i < D) acc = fmaf(xr[i], __ldg(er + lane + 32 * i), acc);
+                    }
+                }
+                if (b < 8) pa[b] = acc; else pb[b - 8] = acc;
+            }
+            const float da = list_reduce8(pa, lane), db = list_reduce8(pb, lane);
+            if (ca < l_bins) argmin_take(bd, bi, ref_distance(xx, da, ea), ca);
+            if (cb < l_bins) argmin_take(bd, bi, ref_distance(xx, db, eb), cb);
+        }
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            argmin_take(bd, bi, od, oi);
+        }
+        if (lane == 0) {
+            const int rel = bi == 0x7fffffff ? 0 : bi;
+            q_rel[row] = rel;
+            q_abs[row] = g * l_bins + rel;
+            if (min_d) min_d[row] = bd;
+            sum += double(bd);
+        }
+    }
+    sum = block_sum(sum, red);
+    if (threadIdx.x == 0 && scalars && sum != 0.0) atomicAdd(&scalars[VQ_S_SUM_MIN_D], sum);
+}
+
 }  // namespace vq

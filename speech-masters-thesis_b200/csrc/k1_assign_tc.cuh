@@ -78,7 +78,6 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
-    int dual_issue;          // two MMA issuer warps (even / odd code tiles): resident codebook, N = 128 batches only
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
 
@@ -150,20 +149,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
         if (sleep_ns) __nanosleep(sleep_ns);
         if (++spins > SPIN_LIMIT) __trap();
     } while (!mbar_try_wait(bar, parity));
-}
-// dual_issue ordering.  The two issuers share the accumulator stages, and an mbarrier parity wait is only meaningful while the
-// waiter is at most ONE phase ahead: before issuer X waits for the release of the stage batch q will use, the other issuer
-// must have got past ITS wait for that stage's previous use (batch q - acc_stages) -- otherwise X could read "parity done"
-// off a barrier that is still two releases behind and overwrite an accumulator nobody has read yet.
-__device__ __forceinline__ void issuer_publish(uint32_t* slot, uint32_t count) {
-    *reinterpret_cast<volatile uint32_t*>(slot) = count;
-    __threadfence_block();
-}
-__device__ __forceinline__ void issuer_wait_for(const uint32_t* slot, uint32_t at_least) {
-    uint32_t spins = 0;
-    while (*reinterpret_cast<const volatile uint32_t*>(slot) < at_least)
-        if (++spins > (SPIN_LIMIT << 6)) __trap();
-    __threadfence_block();
 }
 // One lane of a converged warp.  The single-issuer roles keep their whole loop warp-uniform and predicate only the
 // asynchronous instruction on this, so operands stay in uniform registers (a divergent `if (lane == 0)` region makes the
@@ -393,7 +378,6 @@ struct __align__(16) Smem {           // control block placed after the data sta
     uint64_t b_full[B_RESIDENT_MAX], b_empty[B_RESIDENT_MAX];
     uint64_t a_full[A_BUFS_MAX], a_empty[A_BUFS_MAX], acc_full[ACC_STAGES_MAX], acc_empty[ACC_STAGES_MAX], cand_full[CD], cand_empty[CD];
     uint32_t tmem_base; uint32_t pad0;
-    uint32_t issued[2];  // dual_issue: code-tile batches each MMA issuer has got past the accumulator-empty wait of (its own count)
     alignas(16) float err_c[4];      // [0], [1]: 2 err <= err_c[0] * ||x||^2 + err_c[1] (a-priori bound, linear in ||x||^2: no sqrt in the scan groups)
 };
 // after the control block: Cand cand[cd][2][TM]; float2 rowstat[cd][TM] ((||x||^2, ||x - fp16(x)||^2) of the tiles waiting
@@ -424,11 +408,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
-        for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), p.dual_issue ? 2 : 1); }
+        for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
         for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 4); }
         for (int i = 0; i < CD; ++i) { mbar_init(smem_u32(&ctl->cand_full[i]), 8); mbar_init(smem_u32(&ctl->cand_empty[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ctl->issued[0] = ctl->issued[1] = 0u;
         {
             // err = ||x - x16|| max||e16|| + ||x|| max||e - e16|| + acc_err + 4 ulp  <=  A ||x|| + B   with ||x - x16|| <= 2^-11 (1 + 2^-10) ||x||
             // (+ the sub-normal floor), and ||x|| <= (||x||^2 / c + c) / 2 for any c > 0 (c = max||e16||, the typical frame norm)
@@ -547,16 +530,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
         }
     } else if (warp == W_MMA) {
-        // ============================================================ MMA issuer(s)
-        // dual_issue (resident codebook, N = 128 batches): warp W_MMA issues the even code tiles, warp W_ALLOC the odd ones.
-        // A tcgen05.commit is followed by the next batch's barrier probe in the same warp, and that probe only returns
-        // once the commit has retired, i.e. after the batch's last MMA has FINISHED (measured: ~200 cycles between the
-        // commit and the next probe's return, tools/tc_timeline.py) -- a single issuer therefore lets the tensor pipe run
-        // dry at every batch boundary.  With two issuers one warp's drain overlaps the other warp's MMAs.
+        // ============================================================ MMA issuer
+        // (Tried in round 2 and removed: a second issuer warp taking the odd code tiles, on the theory that the barrier probe
+        //  after a tcgen05.commit only returns once the batch has drained.  Measured equal: 0.0752 vs 0.0754 ms.)
         reg_dec<REGS_ISSUER>();
         {
             const bool leader = elect_one();
-            const bool dual = p.dual_issue != 0;
             uint32_t qa = 0, it = 0;
             Ring ra, rb;                                      // A buffers; streaming B stages
             // loop-invariant operands of the resident fast path
@@ -603,11 +582,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                     } else {
                         for (int nt = 0; nt < n_nt; ++nt, ++qa, rs.next(acc_stages)) {
-                            if (dual && (nt & 1)) continue;             // odd code tiles: the second issuer (warp W_ALLOC)
                             const uint32_t st = rs.i, sph = rs.ph;
-                            if (dual && qa >= acc_stages) issuer_wait_for(&ctl->issued[(qa - acc_stages) & 1u], ((qa - acc_stages) >> 1) + 1u);
                             mbar_spin(smem_u32(&ctl->acc_empty[st]), sph ^ 1);
-                            if (dual) issuer_publish(&ctl->issued[0], (qa >> 1) + 1u);
                             tc_fence_after();
                             VQ_TRACE_NT(10, it, nt);
                             if (leader) {
@@ -713,60 +689,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     if (leader) tc_commit(smem_u32(&ctl->acc_full[s]));
                     VQ_TRACE_NT(11, it, nt);
                 }
-                if (dual) {                                   // (first tile: this warp issued the odd code tiles too)
-                    issuer_publish(&ctl->issued[0], qa >> 1);
-                    issuer_publish(&ctl->issued[1], qa >> 1);
-                }
                 if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
                 VQ_TRACE(2, it);
-            }
-        }
-    } else if (warp == W_ALLOC) {
-        // ============================================================ second MMA issuer (dual_issue): the odd code tiles
-        reg_dec<REGS_ISSUER>();
-        if (p.dual_issue) {
-            const bool leader = elect_one();
-            Ring ra, rs;
-            const uint64_t bd0 = b_desc_base(smem_u32(bs_base));
-            const uint64_t kb_stride = uint64_t(p.n_nt) * uint64_t(B_STAGE_BYTES >> 4);
-            const uint64_t hd0 = hn_desc(smem_u32(hn_b));
-            const uint32_t a_const = tmem + uint32_t(p.a_const_col);
-            const uint64_t ac_desc = aconst_desc(smem_u32(hn_b + size_t(p.n_nt) * HN_TILE_BYTES));
-            const bool const_smem = p.const_smem != 0, fold = p.fold != 0;
-            const uint32_t acc_stages = uint32_t(p.acc_stages), a_bufs = uint32_t(p.a_bufs);
-            const int n_kb = p.n_kb, n_nt = p.n_nt;
-            bool first_tile = true;
-            uint32_t qa = 0;
-            for (int tile = first; tile < p.n_tiles; tile += step, ra.next(a_bufs), first_tile = false) {
-                const uint32_t a = ra.i;
-                if (first_tile) {
-                    // the B tiles are still landing: warp W_MMA issues all of the first tile.  This commit has no MMA of
-                    // this thread to wait for and arrives at once.
-                    for (int nt = 0; nt < n_nt; ++nt, ++qa) rs.next(acc_stages);
-                    if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
-                    continue;
-                }
-                mbar_spin(smem_u32(&ctl->a_full[a]), ra.ph);
-                tc_fence_after();
-                const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
-                for (int nt = 0; nt < n_nt; ++nt, ++qa, rs.next(acc_stages)) {
-                    if (!(nt & 1)) continue;
-                    const uint32_t st = rs.i;
-                    if (qa >= acc_stages) issuer_wait_for(&ctl->issued[(qa - acc_stages) & 1u], ((qa - acc_stages) >> 1) + 1u);
-                    mbar_spin(smem_u32(&ctl->acc_empty[st]), rs.ph ^ 1);
-                    issuer_publish(&ctl->issued[1], (qa >> 1) + 1u);
-                    tc_fence_after();
-                    if (leader) {
-                        issue_batch_n<IDESC>(n_kb, tmem + st * TN, a_tmem, bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4), kb_stride);
-                        if (fold) {
-                            if (const_smem) tc_mma_ss(tmem + st * TN, ac_desc, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
-                            else tc_mma_ts(tmem + st * TN, a_const, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
-                        }
-                        tc_commit(smem_u32(&ctl->acc_full[st]));
-                    }
-                    __syncwarp();
-                }
-                if (leader) tc_commit(smem_u32(&ctl->a_empty[a]));
             }
         }
     } else if (warp < 4) {
@@ -1026,6 +950,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
             if (warp == 4) VQ_TRACE(9, it);
         }
+    } else {
+        reg_dec<REGS_ISSUER>();                                     // W_ALLOC: idle until the end
     }
 
     tc_fence_before();
@@ -1064,15 +990,14 @@ inline EncodeTiledFn encode_tiled_fn() {
 }  // namespace tc
 
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
-// VQ_K1_SCAN_SLEEP=<ns>, VQ_K1_DUAL=0 (single MMA issuer).  -1 = not set.
+// VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, dual = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
         if (const char* e = getenv("VQ_K1_PAIR")) pair = atoi(e);
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
-        if (const char* e = getenv("VQ_K1_DUAL")) dual = atoi(e);
     }
 };
 inline const TcEnv& tc_env() {
@@ -1124,9 +1049,6 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
-    p.dual_issue = 0;    // opt-in (VQ_K1_DUAL=1): measured equal to the single issuer (0.0752 vs 0.0754 ms), so off by default
-    const bool dual_possible = p.resident && !p.pair && p.n_nt >= 2 && p.n_nt % 2 == 0;   // (even: code-tile parity == batch parity)
-    if (tc_env().dual > 0 && dual_possible) p.dual_issue = 1;
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
     if (p.a_bufs < 1) return "emb_width > 512 (the FP16 A operand must fit the TMEM columns next to the accumulators)";

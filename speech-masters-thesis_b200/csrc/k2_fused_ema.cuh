@@ -6,12 +6,15 @@
 //
 // Work unit = 64 frames x 64 depths.  A CTA owns ONE 64-deep depth slice (blockIdx.y) and a private [K][64] FP32 slab of
 // per-code sums in shared memory (128 KB at K = 512) next to a three-stage ring of x tiles and a two-stage ring of gathered
-// codebook rows (87 KB); the CTAs of a slice stride over the frame tiles.  Each tile's frames are sorted by code (one warp,
-// bitonic, one tile ahead); a run of equal codes is summed in registers (lane == depth) by the warp in whose row range it
-// starts and added to the slab with ONE non-atomic read-modify-write, so a hot code costs one update per tile, not one per
-// frame, and no two warps touch the same slab row in the same tile.  The slab is flushed once per CTA with FP32 reductions.
-// (First version of this kernel kept the accumulators in tensor memory -- 128 lanes x 512 columns is exactly [D][K] -- but
-//  single-column tcgen05.ld / st cost ~100 cycles each whatever their size: 0.32 ms against 0.098 ms for K2 alone.)
+// codebook rows (87 KB); the CTAs of a slice stride over the frame tiles.  "Owner computes": warp w owns the codes with
+// code % 16 == w, so no two warps ever touch the same slab row and no atomics are needed.  Per tile a warp finds its frames
+// with two ballots, groups equal codes with a match (ballot on code == c), sums a group in registers (lane == depth; the
+// loads of a group are independent) and adds it to the slab with ONE read-modify-write -- a hot code costs one update per
+// tile, not one per frame.  The slab is flushed once per CTA with FP32 reductions.
+// Measured history (K = 512, D = 128, 256 utterances; K2 alone 0.098 ms, K3a alone 0.095 ms):
+//   accumulators in tensor memory (128 lanes x 512 columns is exactly [D][K]): single-column tcgen05.ld / st cost ~100
+//   cycles each whatever their size -- 0.32 ms;  sorted runs (one warp bitonic-sorts the next tile, as the standalone K3a
+//   does): the sort is a ~2000-cycle latency chain per 64 x 64 unit that the lock-step iterations cannot hide -- 0.187 ms.
 #pragma once
 #include "k2_gather.cuh"
 
@@ -25,9 +28,8 @@ constexpr int FE_XS = G_TT + 4;                      // row stride of the x tile
 constexpr int FE_NX = 3, FE_NE = 2;                  // x stages (two tiles in flight), gathered-row stages
 constexpr int FE_TILE_FLOATS = FE_DS * FE_XS;        // 4352 floats = 17 KB
 constexpr int FE_KMAX = 512;
-constexpr int FE_PER = (G_TT + FE_WARPS - 2) / (FE_WARPS - 1);   // sorted rows per accumulating warp (5): warp 15 sorts
 inline size_t fe_smem_bytes(int K) {
-    return size_t(FE_NX + FE_NE) * FE_TILE_FLOATS * 4 + GA_RING * G_TT * 12 + 2 * G_TT * 4 + (size_t(K) * FE_DS + K) * 4;
+    return size_t(FE_NX + FE_NE) * FE_TILE_FLOATS * 4 + GA_RING * G_TT * 12 + (size_t(K) * FE_DS + K) * 4;
 }
 
 __global__ void __launch_bounds__(FE_THREADS, 1)
@@ -40,8 +42,7 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
     float* es_base = smem + FE_NX * FE_TILE_FLOATS;                                          // [FE_NE][FE_DS][FE_XS]
     int64_t* s_idx = reinterpret_cast<int64_t*>(es_base + FE_NE * FE_TILE_FLOATS);           // [GA_RING][G_TT]
     float* s_mask = reinterpret_cast<float*>(s_idx + GA_RING * G_TT);                        // [GA_RING][G_TT]
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(s_mask + GA_RING * G_TT);                 // [2][G_TT]  (code << 8 | frame), ~0u = no row
-    float* slab = reinterpret_cast<float*>(sorted + 2 * G_TT);                               // [K][FE_DS]
+    float* slab = s_mask + GA_RING * G_TT;                                                   // [K][FE_DS]
     float* s_cnt = slab + size_t(K) * FE_DS;                                                 // [K]  (slice 0 only)
     __shared__ double red[32];
     __shared__ bool is_last;
@@ -104,39 +105,6 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
 #pragma unroll
         for (int db = 0; db < FE_DS / 8; ++db) dst[8 * db * FE_XS] = ev[db];
     };
-    // keys of the unit in ring slot `ring`: (code << 8) | frame for valid frames, ~0u otherwise; bitonic sort in one warp
-    auto sort_unit = [&](int ring, uint32_t* dst) {
-        uint32_t key[2];
-        const bool exists = s_loc[ring].x >= 0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int t = r * 32 + lane;
-            const int64_t ci = s_idx[ring * G_TT + t];
-            key[r] = (exists && s_mask[ring * G_TT + t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
-        }
-#pragma unroll
-        for (int kk = 2; kk <= G_TT; kk <<= 1) {
-#pragma unroll
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                if (j >= 32) {
-                    const uint32_t a = key[0], b = key[1];
-                    key[0] = min(a, b);
-                    key[1] = max(a, b);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
-                        const int i = r * 32 + lane;
-                        const bool up = (i & kk) == 0, lower = (lane & j) == 0;
-                        key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
-                    }
-                }
-            }
-        }
-        dst[lane] = key[0];
-        dst[32 + lane] = key[1];
-    };
-
     double sq = 0.0, sq_all = 0.0, msum_local = 0.0;
 
 #pragma unroll
@@ -149,7 +117,6 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
     for (int j = 0; j < FE_DS / 8; ++j) ev[j] = 0.f;
     gather_ld(0, ev);
     gather_st(0, ev);
-    if (warp == FE_WARPS - 1) sort_unit(0, sorted);
 #pragma unroll
     for (int j = 0; j < FE_NX - 1; ++j) issue(j, j);
 
@@ -158,7 +125,7 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
         gather_ld((it + 1) & (GA_RING - 1), ev);                   // stored at the end of this iteration
         prefetch_im(it + GA_AHEAD, u + GA_AHEAD * step);           // joins the copy group committed by issue() below
         cp_async_wait<FE_NX - 2>();                                // this thread's copies of unit u have landed
-        __syncthreads();                                           // ... everyone's; sorted[it & 1] and Es[it & 1] complete; stage of unit u-1 free
+        __syncthreads();                                           // ... everyone's; Es[it & 1] complete; stage of unit u-1 free
         issue((it + FE_NX - 1) % FE_NX, (it + FE_NX - 1) & (GA_RING - 1));
 
         const int2 cur = s_loc[it & (GA_RING - 1)];
@@ -196,32 +163,33 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
                 sq += double((accf[0] * vv[0] + accf[1] * vv[1]) + (accf[2] * vv[2] + accf[3] * vv[3]));
             }
         }
-        // ---- EMA statistics of this unit (bottleneck.py:64-68): runs of equal codes -> one slab update each
-        if (warp == FE_WARPS - 1) {
-            sort_unit((it + 1) & (GA_RING - 1), sorted + ((it + 1) & 1) * G_TT);   // next unit's keys (its indices landed a wait ago)
-        } else {
-            const uint32_t* keys = sorted + (it & 1) * G_TT;
-            const int lo = warp * FE_PER, hi = min(G_TT, lo + FE_PER);
-            int i = lo;
-            const uint32_t kprev = (lo > 0 && lo < G_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
-            // skip the tail of a run that started in an earlier warp's range
-            while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
-            while (i < hi) {
-                uint32_t key = keys[i];
-                if (key == 0xFFFFFFFFu) break;                                    // sorted: no more valid frames
-                const uint32_t code = key >> 8;
-                float a0 = 0.f, a1 = 0.f, cnt = 0.f;
-                do {                                                              // one run; may continue past hi
-                    const float* col = S + (key & 255u);
-                    if (lane < dn) a0 += col[lane * FE_XS];
-                    if (lane + 32 < dn) a1 += col[(lane + 32) * FE_XS];
-                    cnt += 1.f;
-                    ++i;
-                    key = i < G_TT ? keys[i] : 0xFFFFFFFFu;
-                } while (key != 0xFFFFFFFFu && (key >> 8) == code);
-                slab[size_t(code) * FE_DS + lane] += a0;
-                slab[size_t(code) * FE_DS + lane + 32] += a1;
-                if (first_slice && lane == 0) s_cnt[code] += cnt;
+        // ---- EMA statistics of this unit (bottleneck.py:64-68): this warp's codes (code % 16 == warp), grouped by code
+        {
+            const int64_t* ci = s_idx + (it & (GA_RING - 1)) * G_TT;
+            const int64_t i0 = ci[lane], i1 = ci[lane + 32];
+            const int c0 = (sm[lane] != 0.f && i0 >= 0) ? int(min(i0, int64_t(K - 1))) : -1;
+            const int c1 = (sm[lane + 32] != 0.f && i1 >= 0) ? int(min(i1, int64_t(K - 1))) : -1;
+            unsigned long long mine = (unsigned long long)__ballot_sync(0xffffffffu, c0 >= 0 && (c0 & (FE_WARPS - 1)) == warp) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, c1 >= 0 && (c1 & (FE_WARPS - 1)) == warp) << 32);
+            const float* col0 = S + lane * FE_XS;                     // this lane's two depth rows of the x tile
+            const float* col1 = S + (lane + 32) * FE_XS;
+            while (mine) {                                            // (warp-uniform)
+                const int f = __ffsll((long long)mine) - 1;
+                const int c = f < 32 ? __shfl_sync(0xffffffffu, c0, f) : __shfl_sync(0xffffffffu, c1, f - 32);
+                unsigned long long same = ((unsigned long long)__ballot_sync(0xffffffffu, c0 == c) |
+                                           ((unsigned long long)__ballot_sync(0xffffffffu, c1 == c) << 32));
+                mine &= ~same;
+                const int cnt = __popcll(same);
+                float a0 = 0.f, a1 = 0.f;
+                while (same) {
+                    const int g = __ffsll((long long)same) - 1;
+                    same &= same - 1;
+                    if (lane < dn) a0 += col0[g];
+                    if (lane + 32 < dn) a1 += col1[g];
+                }
+                slab[size_t(c) * FE_DS + lane] += a0;
+                slab[size_t(c) * FE_DS + lane + 32] += a1;
+                if (first_slice && lane == 0) s_cnt[c] += float(cnt);
             }
         }
         gather_st((it + 1) % FE_NE, ev);                           // Es[(it+1) & 1] was last read in iteration it-1

@@ -229,6 +229,36 @@ int vq_assign_debug(const float* x, int64_t N, int64_t D, int64_t T, const float
                        VQ_ALGO_TC, stream, shortlist4, reinterpret_cast<long long*>(trace), trace_tiles);
 }
 
+int vq_assign_grouped(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int n_vocab, int l_bins,
+                      const int64_t* tok, int64_t* q_rel, int64_t* q_abs, float* min_d, double* scalars,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
+    VQ_REQUIRE(n_vocab > 0 && l_bins > 0 && int64_t(n_vocab) * l_bins < (int64_t(1) << 31), "bad group shape");
+    const int K = n_vocab * l_bins;
+    if (check_shape(N, D, T, K)) return 1;
+    if (N * T == 0) return 0;
+    VQ_REQUIRE(x && k && tok && q_rel && q_abs && workspace, "null pointer");
+    VQ_REQUIRE(D <= 512, "emb_width > 512 is not supported by the grouped kernel");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    VQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    AssignWorkspace w = carve_workspace(workspace, N * T, K, int(D));
+    VQ_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see vq_workspace_bytes)");
+    VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
+    codebook_prepare_kernel<<<(w.Kp * 32 + 255) / 256, 256, 0, stream>>>(k, K, int(D), w.Kp, w.Dp, w.ee, w.hn, nullptr, w.hdr);
+    VQ_CUDA_OK(cudaGetLastError());
+    const int grid = int(std::min<int64_t>(16 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
+    const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
+    auto launch = [&](auto kernel) {
+        kernel<<<grid, L_WARPS * 32, 0, stream>>>(x, N, int(D), T, k, (const float*)w.ee, n_vocab, l_bins, tok, q_rel, q_abs, min_d, scalars);
+    };
+    if (vec && D <= 128) launch(assign_grouped_kernel<true, 1>);
+    else if (vec) launch(assign_grouped_kernel<true, 4>);
+    else if (D <= 128) launch(assign_grouped_kernel<false, 1>);
+    else launch(assign_grouped_kernel<false, 4>);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int vq_gather_st_fwd(const float* x, const int64_t* idx, const float* mask, const float* k, int64_t N, int64_t D,
                      int64_t T, int K, float* x_q, double* scalars, float* results, void* stream) {
     if (check_shape(N, D, T, K)) return 1;

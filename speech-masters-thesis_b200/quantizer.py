@@ -111,6 +111,24 @@ def assign(x, k, algo="auto", want_min_d=False, scalars=None):
     return idx, min_d
 
 
+def assign_grouped(x, k, tok, n_vocab, l_bins, scalars=None):
+    """Grouped K1 on an NCT tensor (models/vqtts/bottleneck.py:38-58): returns (q_rel, q_abs), both [N, T] int64."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n, d, t = x.shape
+    q_rel = torch.empty((n, t), dtype=torch.int64, device=x.device)
+    q_abs = torch.empty((n, t), dtype=torch.int64, device=x.device)
+    if n * t == 0:
+        return q_rel, q_abs
+    ws = _Workspace.get(x.device, n, t, n_vocab * l_bins, d)
+    _Workspace._prepared.pop(_Workspace._key(x.device), None)        # this call re-prepares the workspace for another codebook
+    tok = tok.reshape(n, t).to(torch.int64).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.vq_assign_grouped(ptr(x), n, d, t, ptr(k), n_vocab, l_bins, ptr(tok), ptr(q_rel), ptr(q_abs), None, ptr(scalars),
+                                    ptr(ws), ws.numel(), _stream(x)), "vq_assign_grouped")
+    return q_rel, q_abs
+
+
 def decode_nct(idx, k):
     """idx [N,T] int64 -> [N,D,T] fp32 (bottleneck.py:160-169)."""
     lib = _lib.load()
@@ -158,13 +176,17 @@ class _QuantizeST(torch.autograd.Function):
     """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
 
     @staticmethod
-    def forward(ctx, x, mask, k, algo, after_assign, fused_stats):
+    def forward(ctx, x, mask, k, algo, after_assign, fused_stats, group=None):
         lib = _lib.load()
         n, d, t = x.shape
         kk = k.shape[0]
         scalars = torch.zeros(_lib.NUM_SCALARS, dtype=torch.float64, device=x.device)
         results = torch.zeros(_lib.NUM_RESULTS, dtype=torch.float32, device=x.device)
-        idx, _ = assign(x, k, algo)            # indices only; K2 accumulates the `fit` numerator
+        rel = None
+        if group is not None:                  # (tok, n_vocab, l_bins): phoneme-conditioned codebook subsets
+            rel, idx = assign_grouped(x, k, *group)
+        else:
+            idx, _ = assign(x, k, algo)        # indices only; K2 accumulates the `fit` numerator
         if after_assign is not None:
             # EMA statistics (K3a) and their all-reduce are issued here, BEFORE K2: the collective then overlaps K2,
             # which does not depend on it (K1 -> K3a -> {all-reduce || K2} -> K3b)
@@ -182,11 +204,13 @@ class _QuantizeST(torch.autograd.Function):
         else:
             results.fill_(float("nan"))
         ctx.save_for_backward(x, idx, mask, k, scalars)
-        ctx.mark_non_differentiable(idx, scalars, results)
-        return idx, x_q, results[_lib.R_COMMIT], scalars, results
+        if rel is None:
+            rel = idx
+        ctx.mark_non_differentiable(idx, scalars, results, rel)
+        return idx, x_q, results[_lib.R_COMMIT], scalars, results, rel
 
     @staticmethod
-    def backward(ctx, _g_idx, g_xq, g_commit, _g_scalars, _g_results):
+    def backward(ctx, _g_idx, g_xq, g_commit, _g_scalars, _g_results, _g_rel):
         lib = _lib.load()
         x, idx, mask, k, scalars = ctx.saved_tensors
         n, d, t = x.shape
@@ -199,7 +223,7 @@ class _QuantizeST(torch.autograd.Function):
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_bwd(ptr(x), ptr(idx), ptr(mask), ptr(k), ptr(g_xq), ptr(g_commit), ptr(scalars),
                                            n, d, t, k.shape[0], ptr(grad_x), _stream(x)), "vq_gather_st_bwd")
-        return grad_x, None, None, None, None, None
+        return grad_x, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- modules
@@ -435,7 +459,7 @@ class BottleneckBlock(nn.Module):
             fused_stats = torch.zeros(dist.stats_numel(self.k_bins, self.emb_width), dtype=torch.float32, device=x.device)
         elif update_k:
             hook = lambda x_l: pending.append(self._ema_begin(x.detach(), x_l, mask))
-        x_l, x_q, commit_loss, scalars, results = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook, fused_stats)
+        x_l, x_q, commit_loss, scalars, results, _ = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook, fused_stats)
         if update_k:
             if fused_stats is not None:
                 pending.append(self._ema_begin(x.detach(), x_l, mask, stats=fused_stats))
@@ -443,6 +467,42 @@ class BottleneckBlock(nn.Module):
         else:
             update_metrics = {}
         return x_l, x_q, commit_loss, dict(fit=results[_lib.R_FIT], **update_metrics)
+
+
+class GroupedBottleneck(BottleneckBlock):
+    """Drop-in for the phoneme-conditioned quantiser ``models/vqtts/bottleneck.py::Bottleneck``: one codebook of
+    ``n_vocab * l_bins`` codes, frame j only competes among the ``l_bins`` codes of its aligned token.
+
+    ``forward(y_enc [b, c, ty], x_id [b, tx], attn [b, tx, ty], update_k=True)`` ->
+    ``(q_rel [b, ty] int64, y_d [b, c, ty], commit_loss, metrics)`` (vqtts/bottleneck.py:19-77).  Quirks kept: init_k sees all
+    frames, padded ones included (:35-36); the EMA update runs iff ``self.training`` (:62-63); ``fit`` is
+    sum_all(min_d) / l_bins (the reference's (NT,)x(NT,1) broadcast, :54).  One extension: the reference's
+    ``matmul(x_id, attn)`` (:28) only reshapes for b == 1 (it broadcasts to [b, b, ty]); here every utterance is aligned
+    with its own ids, which is that expression for b == 1."""
+
+    def __init__(self, n_vocab: int, l_bins: int, emb_width: int, mu: float, threshold: float, **block_kwargs):
+        super().__init__(k_bins=n_vocab * l_bins, emb_width=emb_width, mu=mu, threshold=threshold, **block_kwargs)
+        self.n_vocab = n_vocab
+        self.l_bins = l_bins
+
+    def forward(self, y_enc, x_id, attn, update_k=True):
+        _require_cuda(y_enc, "y_enc")
+        b, tx, ty = attn.shape
+        mask = attn.sum(1).reshape(b, 1, ty)                                          # :25
+        tok = torch.matmul(x_id.to(attn.dtype).unsqueeze(1), attn).squeeze(1).long()  # :28  [b, ty]
+        x, mask = self._check_input(y_enc, mask)
+        if update_k and not self.init:
+            with torch.no_grad():
+                self._set_codebook(self._restart_rows_nct(x.detach(), None))          # init_k on ALL frames (:35-36)
+        k = (self.k if self.k.dtype == torch.float32 else self.k.float()).contiguous()
+        pending, hook = [], None
+        if self.training:
+            hook = lambda q_abs: pending.append(self._ema_begin(x.detach(), q_abs, mask))
+        q_abs, x_q, commit_loss, scalars, results, q_rel = _QuantizeST.apply(x, mask, k, self.algo, hook, None,
+                                                                             (tok, self.n_vocab, self.l_bins))
+        metrics = self._ema_finish(pending[0], scalars, results) if self.training else {}
+        fit = (scalars[_lib.S_SUM_MIN_D] / self.l_bins).float()                       # :54
+        return q_rel, x_q, commit_loss, dict(fit=fit, **metrics)
 
 
 class Bottleneck(nn.Module):
