@@ -210,6 +210,15 @@ int          vq_host_ctx_set_codebook(vq_host_ctx* ctx, const float* k_host);
 int          vq_encode_host(vq_host_ctx* ctx, const float* x_host, int64_t n_utt, int64_t t_frames,
                             int64_t* idx_host, double* sum_min_d_host);
 
+/* Compact variant for the code dump (scripts/generate_vq_dataset.py:83-90,105-121 keeps q[:ql] of every utterance): same
+ * pipeline, but the indices are packed on the device into RAGGED uint16 codes -- utterance n contributes its first
+ * lengths_host[n] frames (NULL: all t_frames), utterance-major, no padding -- so 2 bytes per valid frame come back instead of
+ * 8 per padded one.  codes_host must hold sum(lengths) uint16 (<= n_utt * t_frames; vq_host_ctx_codes_staging gives a pinned
+ * buffer of max_rows); *total_codes_out (may be NULL) receives sum(lengths).  Needs k_bins <= 65536. */
+uint16_t*    vq_host_ctx_codes_staging(vq_host_ctx* ctx);   /* max_rows uint16, pinned, allocated on first use */
+int          vq_encode_host_u16(vq_host_ctx* ctx, const float* x_host, int64_t n_utt, int64_t t_frames,
+                                const int32_t* lengths_host, uint16_t* codes_host, int64_t* total_codes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ from . import _lib, dist
 from .quantizer import (Bottleneck, BottleneckBlock, GroupedBottleneck, NoBottleneck, NoBottleneckBlock, assign,
                         assign_grouped, decode_nct, gather_rows, invalidate_prepared)
 from .drop_in import patch_reference
+from .codes import CodeShard, CodeShardWriter, HostEncoder
 
 __all__ = ["Bottleneck", "BottleneckBlock", "GroupedBottleneck", "NoBottleneck", "NoBottleneckBlock", "assign", "assign_grouped",
-           "decode_nct", "gather_rows", "invalidate_prepared", "patch_reference", "_lib"]
+           "decode_nct", "gather_rows", "invalidate_prepared", "patch_reference", "CodeShard", "CodeShardWriter", "HostEncoder", "_lib"]

@@ -56,6 +56,8 @@ SIGNATURES = {
     "vq_host_ctx_x_staging": (_c_void_p, [_c_void_p]),
     "vq_host_ctx_idx_staging": (_c_void_p, [_c_void_p]),
     "vq_host_ctx_set_codebook": (_c_int, [_c_void_p, _c_void_p]),
+    "vq_host_ctx_codes_staging": (_c_void_p, [_c_void_p]),
+    "vq_encode_host_u16": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_void_p, _c_void_p, _c_void_p]),
     "vq_encode_host": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_void_p, _c_void_p]),
 }
 

@@ -80,6 +80,16 @@ static int launch_gather(const float* x, const int64_t* idx, const float* mask, 
     return launch_gather_v<MODE, false>(x, idx, mask, k, grad_xq, grad_commit, N, D, T, K, out, scalars, results, stream);
 }
 
+// int64 indices [nn, T] -> ragged uint16 codes: utterance n keeps its first len[n] frames at out[off[n] ..] (what
+// dump_batch_to_pickle's q[:ql] keeps, scripts/generate_vq_dataset.py:83-90) -- 2 bytes per valid frame cross PCIe instead of 8 per padded one.
+__global__ void __launch_bounds__(256) pack_codes_u16_kernel(const int64_t* __restrict__ idx, int64_t T, const int64_t* __restrict__ off,
+                                                            unsigned short* __restrict__ out) {
+    const int64_t n = blockIdx.y;
+    const int64_t len = off[n + 1] - off[n];
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < len; t += int64_t(gridDim.x) * blockDim.x)
+        out[off[n] + t] = static_cast<unsigned short>(idx[n * T + t]);
+}
+
 // ---- optional per-kernel event timing of vq_assign (bench.py roofline)
 namespace {
 constexpr int PROF_RING = 64;
@@ -428,6 +438,12 @@ struct vq_host_ctx {
     double* h_scalars = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
     bool prepared[2] = {false, false};      // workspace b already holds the current codebook's operands
+    // compact-code path (vq_encode_host_u16)
+    unsigned short* d_codes[2] = {nullptr, nullptr};
+    int64_t* d_off[2] = {nullptr, nullptr};
+    int64_t* h_off[2] = {nullptr, nullptr};
+    int64_t off_cap = 0;                    // utterances per chunk the offset buffers hold
+    unsigned short* h_codes = nullptr;
 };
 
 void vq_host_ctx_destroy(vq_host_ctx* c) {
@@ -438,8 +454,9 @@ void vq_host_ctx_destroy(vq_host_ctx* c) {
         cudaFree(c->d_x[i]); cudaFree(c->d_idx[i]); cudaFree(c->d_ws[i]); cudaFree(c->d_scalars[i]);
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     }
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_codes[i]); cudaFree(c->d_off[i]); cudaFreeHost(c->h_off[i]); }
     cudaFree(c->d_k);
-    cudaFreeHost(c->h_x); cudaFreeHost(c->h_idx); cudaFreeHost(c->h_scalars);
+    cudaFreeHost(c->h_x); cudaFreeHost(c->h_idx); cudaFreeHost(c->h_scalars); cudaFreeHost(c->h_codes);
     delete c;
 }
 
@@ -473,6 +490,11 @@ vq_host_ctx* vq_host_ctx_create(int device, int64_t max_rows, int K, int D) {
     return c;
 }
 
+uint16_t* vq_host_ctx_codes_staging(vq_host_ctx* c) {
+    if (!c) return nullptr;
+    if (!c->h_codes && cudaMallocHost(&c->h_codes, size_t(c->max_rows) * 2) != cudaSuccess) { fail("vq_host_ctx_codes_staging: allocation failed%s"); return nullptr; }
+    return c->h_codes;
+}
 float* vq_host_ctx_x_staging(vq_host_ctx* c) { return c ? c->h_x : nullptr; }
 int64_t* vq_host_ctx_idx_staging(vq_host_ctx* c) { return c ? c->h_idx : nullptr; }
 
@@ -537,6 +559,79 @@ int vq_encode_host(vq_host_ctx* c, const float* x_host, int64_t N, int64_t T, in
     }
     cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
     if (sum_min_d_host) *sum_min_d_host = total;
+    return rc;
+}
+
+int vq_encode_host_u16(vq_host_ctx* c, const float* x_host, int64_t N, int64_t T, const int32_t* lengths_host,
+                       uint16_t* codes_host, int64_t* total_codes_out) {
+    VQ_REQUIRE(c && x_host && codes_host, "null pointer");
+    VQ_REQUIRE(N >= 0 && T >= 0 && N * T <= c->max_rows, "job larger than the context was created for");
+    VQ_REQUIRE(c->K <= 65536, "codes do not fit 16 bits (k_bins > 65536)");
+    VQ_CUDA_OK(cudaSetDevice(c->device));
+    if (total_codes_out) *total_codes_out = 0;
+    if (N * T == 0) return 0;
+    const int64_t bytes_per_utt = int64_t(c->D) * T * 4;
+    int64_t utt_per_chunk = std::max<int64_t>(1, (int64_t(32) << 20) / std::max<int64_t>(1, bytes_per_utt));
+    utt_per_chunk = std::min(utt_per_chunk, N);
+    const int64_t n_chunks = (N + utt_per_chunk - 1) / utt_per_chunk;
+    for (int i = 0; i < 2; ++i)
+        if (!c->d_codes[i]) VQ_CUDA_OK(cudaMalloc(&c->d_codes[i], size_t(c->chunk_rows) * 2));
+    if (c->off_cap < utt_per_chunk + 1) {
+        for (int i = 0; i < 2; ++i) {
+            VQ_CUDA_OK(cudaStreamSynchronize(c->streams[i]));
+            cudaFree(c->d_off[i]); cudaFreeHost(c->h_off[i]);
+            c->d_off[i] = nullptr; c->h_off[i] = nullptr;
+            VQ_CUDA_OK(cudaMalloc(&c->d_off[i], size_t(utt_per_chunk + 1) * 8));
+            VQ_CUDA_OK(cudaMallocHost(&c->h_off[i], size_t(utt_per_chunk + 1) * 8));
+        }
+        c->off_cap = utt_per_chunk + 1;
+    }
+    cudaEvent_t done[2];
+    VQ_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    VQ_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int rc = 0;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && !rc) {
+            snprintf(err_buf(), 512, "vq_encode_host_u16: %s failed: %s", what, cudaGetErrorString(e));
+            rc = 1;
+        }
+        return e == cudaSuccess;
+    };
+    int64_t written = 0;                      // codes of the chunks issued so far
+    for (int64_t ci = 0; ci < n_chunks && !rc; ++ci) {
+        const int b = int(ci & 1);
+        cudaStream_t s = c->streams[b];
+        const int64_t n0 = ci * utt_per_chunk, nn = std::min(utt_per_chunk, N - n0);
+        if (ci >= 2 && !cuda_ok(cudaEventSynchronize(done[b]), "cudaEventSynchronize")) break;   // buffer b (and its pinned offsets) free again
+        int64_t* off = c->h_off[b];
+        off[0] = 0;
+        for (int64_t i = 0; i < nn; ++i) {
+            int64_t len = lengths_host ? int64_t(lengths_host[n0 + i]) : T;
+            if (len < 0 || len > T) { rc = fail("vq_encode_host_u16: a length is outside [0, T]%s"); break; }
+            off[i + 1] = off[i] + len;
+        }
+        if (rc) break;
+        const int64_t chunk_codes = off[nn];
+        if (!cuda_ok(cudaMemcpyAsync(c->d_x[b], x_host + n0 * int64_t(c->D) * T, size_t(nn) * bytes_per_utt, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(x)")) break;
+        if (!cuda_ok(cudaMemcpyAsync(c->d_off[b], off, size_t(nn + 1) * 8, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(offsets)")) break;
+        if (vq_assign(c->d_x[b], nn, c->D, T, c->d_k, c->K, c->d_idx[b], nullptr, nullptr, c->d_ws[b], c->ws_bytes,
+                      VQ_ALGO_AUTO | (c->prepared[b] ? VQ_ALGO_PREPARED : 0), s)) { rc = 1; break; }
+        c->prepared[b] = true;
+        if (chunk_codes > 0) {
+            const dim3 grid(unsigned(std::min<int64_t>((T + 255) / 256, 64)), unsigned(nn));
+            pack_codes_u16_kernel<<<grid, 256, 0, s>>>(c->d_idx[b], T, c->d_off[b], c->d_codes[b]);
+            if (!cuda_ok(cudaGetLastError(), "pack_codes_u16_kernel")) break;
+            if (!cuda_ok(cudaMemcpyAsync(codes_host + written, c->d_codes[b], size_t(chunk_codes) * 2, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(codes)")) break;
+        }
+        written += chunk_codes;
+        if (!cuda_ok(cudaEventRecord(done[b], s), "cudaEventRecord")) break;
+    }
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaStreamSynchronize(c->streams[b]);
+        if (e != cudaSuccess && !rc) rc = fail("vq_encode_host_u16: %s", cudaGetErrorString(e));
+    }
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    if (total_codes_out) *total_codes_out = written;
     return rc;
 }
 

@@ -136,3 +136,40 @@ def test_grouped_raw_entry_point(vq):
     assert torch.equal(q_abs.cpu().reshape(-1), tok.reshape(-1) * l_bins + o_rel)
     close(min_d.cpu().reshape(-1), o_min, rtol=1e-5, atol=1e-5)
     close(float(scalars[0]), float(o_min.double().sum()), rtol=1e-5)
+
+
+def test_host_encoder_and_code_shard_round_trip(vq, tmp_path):
+    """latents on the host -> ragged uint16 codes (vq_encode_host_u16) -> one binary shard -> what
+    ``dump_batch_to_pickle`` would have pickled (q[:ql] of every utterance, scripts/generate_vq_dataset.py:86-87), on the
+    golden encode case produced by the unmodified reference plus a multi-chunk LJSpeech-like batch vs the oracle."""
+    z = np.load(os.path.join(GOLDEN, "encode_k512_d128.npz"))
+    g = {k: z[k] for k in z.files}
+    ql = g["mask"].sum(axis=(1, 2)).astype(np.int32)
+    enc = vq.HostEncoder(0, 300 * 1800, g["k0"])
+    codes, lengths = enc.encode(g["x"], ql)
+    want = np.concatenate([g["z"][i, :ql[i]] for i in range(len(ql))])
+    gap = g["gap"].reshape(g["z"].shape)
+    safe = np.concatenate([gap[i, :ql[i]] for i in range(len(ql))]) > 1e-3
+    assert codes.dtype == np.uint16 and codes.size == int(ql.sum()) and np.array_equal(codes[safe], want[safe])
+    w = vq.CodeShardWriter(str(tmp_path / "val.vqb2"), vocab_size=512)
+    w.append_batch(codes, lengths)
+    w.close()
+    shard = vq.CodeShard(str(tmp_path / "val.vqb2"))
+    for i in range(len(ql)):
+        assert np.array_equal(np.asarray(shard[i]["q"])[gap[i, :ql[i]] > 1e-3], g["z"][i, :ql[i]][gap[i, :ql[i]] > 1e-3])
+    # a batch large enough for several chunks, filled in place in the pinned staging view
+    gen = torch.Generator().manual_seed(3)
+    code = T(g["k0"])
+    lens = O.ljspeech_like_lengths(150, gen)
+    x, mask = O.synthetic_batch(lens, 128, gen, codebook=code)
+    stage = enc.x_staging(*[x.shape[0], x.shape[2]])
+    stage[...] = x.numpy()
+    codes, lengths = enc.encode(stage, lens.numpy().astype(np.int32))
+    rows = x.permute(0, 2, 1).reshape(-1, 128)
+    o_l, _ = O.assign_chunked(rows, code)
+    o_l = o_l.view(x.shape[0], x.shape[2])
+    want = torch.cat([o_l[i, :int(lens[i])] for i in range(len(lens))])
+    valid_rows = torch.cat([rows.view(x.shape[0], x.shape[2], 128)[i, :int(lens[i])] for i in range(len(lens))])
+    rep = O.audit_indices(valid_rows, code, want, torch.from_numpy(codes.astype(np.int64)))
+    assert rep["rows"] == int(lens.sum()) and rep["errors"] == 0, rep
+    enc.close()
