@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "k1_prepare.cuh"
 #include "vq_common.cuh"
@@ -78,6 +79,7 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
+    int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
 
@@ -342,6 +344,14 @@ __device__ __forceinline__ void issue_batch(uint32_t d_tmem, uint32_t a_tmem, ui
             tc_mma_ts(d_tmem, a_tmem + uint32_t(kb * (BKB / 2) + k4 * 8), b + uint64_t(kb) * kb_stride + uint64_t(k4 * 2), IDESC_,
                       (kb | k4) != 0 ? 1u : 0u);
 }
+// MMAs J0 .. J1-1 of a batch (j = 4 kb + k4), straight-line
+template <int J0, int J1, uint32_t IDESC_>
+__device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint64_t kb_stride) {
+#pragma unroll
+    for (int j = J0; j < J1; ++j)
+        tc_mma_ts(d_tmem, a_tmem + uint32_t((j >> 2) * (BKB / 2) + (j & 3) * 8), b + uint64_t(j >> 2) * kb_stride + uint64_t((j & 3) * 2), IDESC_,
+                  j != 0 ? 1u : 0u);
+}
 template <uint32_t IDESC_>
 __device__ __forceinline__ void issue_batch_n(int n_kb, uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint64_t kb_stride) {
     switch (n_kb) {
@@ -557,6 +567,62 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
 #if !(VQ_EXPERIMENT & (16 | 64 | 128))
+                if (resident && !pair && it != 0 && p.pipe_issue && (n_kb == 1 || n_kb == 2 || n_kb == 4)) {
+                    // Software-pipelined steady state (N = 128 batches).  The tensor core's queue is only a couple of
+                    // instructions deep, so the ~40 scalar instructions between two batches (barrier probe, ring arithmetic,
+                    // descriptors; ~200 cycles on this single warp, ~650 at a tile boundary) were bubbles in the tensor pipe.
+                    // Here the NEXT batch's wait and bookkeeping run while the last two MMAs of the current batch are still
+                    // to be issued, i.e. while the queue is full; the first MMA of the next batch then follows the commit at once.
+                    auto steady = [&](auto nkb_tag) {
+                        constexpr int NJ = 4 * decltype(nkb_tag)::value;          // MMAs per batch (without the folded step)
+                        int nt = 0, tile_c = tile;
+                        uint32_t a_tmem_c = a_tmem;
+                        mbar_spin(smem_u32(&ctl->acc_empty[rs.i]), rs.ph ^ 1);
+                        tc_fence_after();
+                        for (;;) {
+                            const uint32_t st = rs.i;
+                            const uint32_t d_tmem = tmem + st * TN;
+                            const uint64_t b = bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4);
+                            if (leader) issue_part<0, NJ - 2, IDESC>(d_tmem, a_tmem_c, b, kb_stride);
+                            // ---- the next batch: which tile / A buffer / accumulator stage, and wait for them
+                            Ring rs_n = rs, ra_n = ra;
+                            rs_n.next(acc_stages);
+                            int nt_n = nt + 1, tile_n = tile_c;
+                            uint32_t a_tmem_n = a_tmem_c;
+                            const bool last = nt_n == n_nt;
+                            bool more = true;
+                            if (last) {
+                                nt_n = 0;
+                                tile_n = tile_c + step;
+                                more = tile_n < p.n_tiles;
+                                if (more) {
+                                    ra_n.next(a_bufs);
+                                    mbar_spin(smem_u32(&ctl->a_full[ra_n.i]), ra_n.ph);
+                                    a_tmem_n = tmem + a_col0 + ra_n.i * a_stride;
+                                }
+                            }
+                            if (more) mbar_spin(smem_u32(&ctl->acc_empty[rs_n.i]), rs_n.ph ^ 1);
+                            tc_fence_after();
+                            // ---- finish the current batch
+                            if (leader) {
+                                issue_part<NJ - 2, NJ, IDESC>(d_tmem, a_tmem_c, b, kb_stride);
+                                if (fold) {
+                                    if (const_smem) tc_mma_ss(d_tmem, ac_desc, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
+                                    else tc_mma_ts(d_tmem, a_const, hd0 + uint64_t(nt) * uint64_t(HN_TILE_BYTES >> 4), IDESC, 1u);
+                                }
+                                tc_commit(smem_u32(&ctl->acc_full[st]));
+                                if (last) tc_commit(smem_u32(&ctl->a_empty[ra.i]));
+                            }
+                            __syncwarp();
+                            if (!more) break;
+                            rs = rs_n; ra = ra_n; nt = nt_n; tile_c = tile_n; a_tmem_c = a_tmem_n;
+                        }
+                    };
+                    if (n_kb == 1) steady(std::integral_constant<int, 1>());
+                    else if (n_kb == 2) steady(std::integral_constant<int, 2>());
+                    else steady(std::integral_constant<int, 4>());
+                    break;                                    // every remaining tile of this CTA has been issued
+                }
                 if (resident && it != 0) {
                     // Steady state with the codebook resident in shared memory (every B tile is known to have landed after
                     // the first frame tile): nothing but barrier waits between straight-line MMA batches.
@@ -992,12 +1058,13 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
 // VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
         if (const char* e = getenv("VQ_K1_PAIR")) pair = atoi(e);
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
+        if (const char* e = getenv("VQ_K1_PIPE")) pipe = atoi(e);
     }
 };
 inline const TcEnv& tc_env() {
@@ -1049,6 +1116,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
+    p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
     if (p.a_bufs < 1) return "emb_width > 512 (the FP16 A operand must fit the TMEM columns next to the accumulators)";
