@@ -6,8 +6,9 @@
 //
 // Work unit = 64 frames x 64 depths.  A CTA owns ONE 64-deep depth slice (blockIdx.y) and a private [K][64] FP32 slab of
 // per-code sums in shared memory (128 KB at K = 512) next to a three-stage ring of x tiles and a two-stage ring of gathered
-// codebook rows (87 KB); the CTAs of a slice stride over the frame tiles.  "Owner computes": warp w owns the codes with
-// code % 16 == w, so no two warps ever touch the same slab row and no atomics are needed.  Per tile a warp finds its frames
+// codebook rows (87 KB); the CTAs of a slice stride over the frame tiles.  4 warps do the straight-through arithmetic while
+// the other 12 do the statistics ("owner computes": warp w owns the codes with code % 12 == w, so no two warps ever touch
+// the same slab row and no atomics are needed).  Per tile a warp finds its frames
 // with two ballots, groups equal codes with a match (ballot on code == c), sums a group in registers (lane == depth; the
 // loads of a group are independent) and adds it to the slab with ONE read-modify-write -- a hot code costs one update per
 // tile, not one per frame.  The slab is flushed once per CTA with FP32 reductions.
@@ -26,6 +27,8 @@ constexpr int FE_DS = 64;                            // depths per work unit (= 
 constexpr int FE_XS = G_TT + 4;                      // row stride of the x tile and of the gathered rows (68 floats: 16-byte aligned rows,
                                                      // lane == depth reads of one frame are 4-way bank conflicts instead of 32-way)
 constexpr int FE_NX = 3, FE_NE = 2;                  // x stages (two tiles in flight), gathered-row stages
+constexpr int FE_CW = 4;                             // warps 0 .. FE_CW-1: straight-through arithmetic; the other FE_OW warps: EMA statistics
+constexpr int FE_OW = FE_WARPS - FE_CW;              // (between the same two barriers, so an iteration costs max(), not sum(), of the two)
 constexpr int FE_TILE_FLOATS = FE_DS * FE_XS;        // 4352 floats = 17 KB
 constexpr int FE_KMAX = 512;
 inline size_t fe_smem_bytes(int K) {
@@ -134,8 +137,8 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
         const float* S = xs_base + size_t(it % FE_NX) * FE_TILE_FLOATS;
         const float* Es = es_base + size_t(it % FE_NE) * FE_TILE_FLOATS;
         const float* sm = s_mask + (it & (GA_RING - 1)) * G_TT;
-        // ---- straight-through output + loss reductions (bottleneck.py:194-201)
-        {
+        // ---- straight-through output + loss reductions (bottleneck.py:194-201): warps 0 .. FE_CW-1
+        if (warp < FE_CW) {
             const int t4 = (tid & 15) * 4, dg = tid >> 4;
             if (first_slice && tid < G_TT) msum_local += double(sm[tid]);
             if (t4 < tt) {
@@ -145,7 +148,7 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
                 float accf[4] = {0.f, 0.f, 0.f, 0.f};
                 float* dst = out + (int64_t(n) * D + d0) * T + t0 + t4;
 #pragma unroll
-                for (int d = dg; d < dn; d += FE_THREADS / 16) {
+                for (int d = dg; d < dn; d += FE_CW * 2) {
                     const float4 e4 = *reinterpret_cast<const float4*>(Es + d * FE_XS + t4);
                     const float4 x4 = *reinterpret_cast<const float4*>(S + d * FE_XS + t4);
                     const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
@@ -163,14 +166,15 @@ gather_fwd_ema_kernel(const float* __restrict__ x, const int64_t* __restrict__ i
                 sq += double((accf[0] * vv[0] + accf[1] * vv[1]) + (accf[2] * vv[2] + accf[3] * vv[3]));
             }
         }
-        // ---- EMA statistics of this unit (bottleneck.py:64-68): this warp's codes (code % 16 == warp), grouped by code
-        {
+        // ---- EMA statistics of this unit (bottleneck.py:64-68): warp FE_CW + w owns the codes with code % FE_OW == w
+        else {
+            const int ow = warp - FE_CW;
             const int64_t* ci = s_idx + (it & (GA_RING - 1)) * G_TT;
             const int64_t i0 = ci[lane], i1 = ci[lane + 32];
             const int c0 = (sm[lane] != 0.f && i0 >= 0) ? int(min(i0, int64_t(K - 1))) : -1;
             const int c1 = (sm[lane + 32] != 0.f && i1 >= 0) ? int(min(i1, int64_t(K - 1))) : -1;
-            unsigned long long mine = (unsigned long long)__ballot_sync(0xffffffffu, c0 >= 0 && (c0 & (FE_WARPS - 1)) == warp) |
-                                      ((unsigned long long)__ballot_sync(0xffffffffu, c1 >= 0 && (c1 & (FE_WARPS - 1)) == warp) << 32);
+            unsigned long long mine = (unsigned long long)__ballot_sync(0xffffffffu, c0 >= 0 && c0 % FE_OW == ow) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, c1 >= 0 && c1 % FE_OW == ow) << 32);
             const float* col0 = S + lane * FE_XS;                     // this lane's two depth rows of the x tile
             const float* col1 = S + (lane + 32) * FE_XS;
             while (mine) {                                            // (warp-uniform)

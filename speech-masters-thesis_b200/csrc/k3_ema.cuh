@@ -105,7 +105,9 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
         int64_t k = s_scan;
         while (count <= ER_LIST - 32 && k < n_mine) {
             const int64_t kk = k + lane;
-            const int64_t tile = first + kk * step;
+            // LAST tiles first: in the training forward this kernel follows K1, which streamed x front to back, so the tail of x
+            // is what the 126 MB L2 still holds (and K2, which follows, starts at the front -- what this kernel touched last)
+            const int64_t tile = first + (n_mine - 1 - kk) * step;
             const bool ok = kk < n_mine && (tile_flags == nullptr || tile_flags[tile] != 0);
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (ok) {

@@ -31,6 +31,7 @@ def T(a, dev=None):
 
 def close(a, b, rtol=1e-5, atol=1e-7):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else b
     np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
 
 

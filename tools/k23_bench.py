@@ -42,6 +42,8 @@ def main():
     calls = {
         "k2_fwd": (lambda: lib.vq_gather_st_fwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K, x_q.data_ptr(),
                                                 scalars.data_ptr(), res.data_ptr(), stream), rows * (8 * D + 12)),
+        "k2_fused": (lambda: lib.vq_gather_st_fwd_ema(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), n, d, t, K, x_q.data_ptr(),
+                                                      scalars.data_ptr(), res.data_ptr(), stats.data_ptr(), stream), rows * (8 * D + 12) + 4 * K * (D + 1)),
         "k2_bwd": (lambda: lib.vq_gather_st_bwd(xd.data_ptr(), idx.data_ptr(), md.data_ptr(), kd.data_ptr(), g_in.data_ptr(),
                                                 g_commit.data_ptr(), scalars.data_ptr(), n, d, t, K, x_q.data_ptr(), stream), rows * (12 * D + 12)),
         "k2_dec": (lambda: lib.vq_decode(idx.data_ptr(), kd.data_ptr(), n, d, t, K, x_q.data_ptr(), stream), rows * (4 * D + 8)),
