@@ -488,7 +488,7 @@ def run_b200(args):
 
     rooflines = [
         hbm_line("K2 vq_gather_st_fwd", k2_fwd, rows * (8 * EMB + 12)),
-        hbm_line("K2+K3a vq_gather_st_fwd_ema (fused; what the training forward runs)", k2_fused, rows * (8 * EMB + 12) + 4 * K_BINS * (EMB + 1)),
+        hbm_line("K2+K3a vq_gather_st_fwd_ema (fused, opt-in: slower than K2 + K3a apart)", k2_fused, rows * (8 * EMB + 12) + 4 * K_BINS * (EMB + 1)),
         hbm_line("K2 vq_gather_st_bwd", k2_bwd, rows * (12 * EMB + 12)),
         hbm_line("K2 vq_decode", k2_dec, rows * (4 * EMB + 8)),
         hbm_line("K3a vq_ema_accumulate", k3_acc, valid_frames * (4 * EMB + 8) + rows * 4 + 4 * K_BINS * (EMB + 1)),

@@ -79,6 +79,7 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
+    int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
@@ -144,6 +145,22 @@ struct TileWalk {
     __device__ __forceinline__ TileWalk(int tile, int per) : n(tile / per), t(tile % per) {}
     __device__ __forceinline__ void advance(int step, int per) { t += step; while (t >= per) { t -= per; ++n; } }
 };
+// Long waits of a single-lane role (the MMA issuer waiting for the next converted tile, thousands of cycles): probing in a
+// tight loop costs ~5 issued instructions every ~20 cycles on a scheduler the front and scan warps need (ncu: branches and
+// barrier probes were a third of all issued instructions).  mode 0: tight test_wait loop, 1: suspending try_wait,
+// 2: test_wait with a short nanosleep between probes.
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int mode) {
+    if (mode == 1) { mbar_wait<0>(bar, parity); return; }
+    if (mode == 0) { mbar_spin(bar, parity); return; }
+    uint32_t ok = 0, spins = 0;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(40);
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
@@ -562,7 +579,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const uint32_t a_bufs = uint32_t(p.a_bufs);
             for (int tile = first; tile < p.n_tiles; tile += step, ++it, ra.next(a_bufs)) {
                 const uint32_t a = ra.i, aph = ra.ph;
-                mbar_spin(smem_u32(&ctl->a_full[a]), aph);
+                mbar_wait_mode(smem_u32(&ctl->a_full[a]), aph, p.await_mode);
                 tc_fence_after();
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
@@ -597,7 +614,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                 more = tile_n < p.n_tiles;
                                 if (more) {
                                     ra_n.next(a_bufs);
-                                    mbar_spin(smem_u32(&ctl->a_full[ra_n.i]), ra_n.ph);
+                                    mbar_wait_mode(smem_u32(&ctl->a_full[ra_n.i]), ra_n.ph, p.await_mode);
                                     a_tmem_n = tmem + a_col0 + ra_n.i * a_stride;
                                 }
                             }
@@ -1058,13 +1075,14 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
 // VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
         if (const char* e = getenv("VQ_K1_PAIR")) pair = atoi(e);
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
         if (const char* e = getenv("VQ_K1_PIPE")) pipe = atoi(e);
+        if (const char* e = getenv("VQ_K1_AWAIT")) await = atoi(e);
     }
 };
 inline const TcEnv& tc_env() {
@@ -1116,6 +1134,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
+    p.await_mode = tc_env().await >= 0 ? tc_env().await : 0;
     p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns

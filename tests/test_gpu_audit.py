@@ -136,12 +136,12 @@ def test_fused_forward_ema_matches_separate_kernels(vq, shape):
     x, mask = O.synthetic_batch(lengths, D, gen, codebook=code if clustered else None)
     xd, md, kd = x.to(DEV), mask.to(DEV), code.to(DEV)
     outs = []
-    for fuse in (None, False):
+    for fuse in (True, False):
         blk = vq.BottleneckBlock(K, D, 0.99, 1.0).to(DEV)
         blk.fuse_ema = fuse
         blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 2, torch.full((K,), 2.0, device=DEV), True
         blk.train()
-        assert blk._fuse_ema_ok(xd) == (fuse is None)
+        assert blk._fuse_ema_ok(xd) == fuse
         torch.manual_seed(3)
         x_l, x_q, commit, metrics = blk(xd, md, update_k=True)
         outs.append((x_l.cpu(), x_q.cpu(), float(commit), blk.k.cpu(), blk.k_sum.cpu(), blk.k_elem.cpu(),
