@@ -369,9 +369,32 @@ def run_b200(args):
         fwd_graph_ms = None
     del blk
 
-    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms, fwd_graph_ms if fwd_graph_ms else 0.0, sus_ms, g_ms],
+    # ---- BASELINE.json configs[4]: quantise + index gather for 256 utterances IN TOTAL (256 / world per GPU), through the module
+    # API (BottleneckBlock.encode + .decode: what TransformerLM.reconstruct / sample consume, transformer_lm.py:101-108)
+    per_rank = max(1, UTT_PER_STEP // world)
+    eblk = vqb200.BottleneckBlock(K_BINS, EMB, 0.99, 1.0).to(dev)
+    eblk.k, eblk.init = kd.clone(), True
+    eblk.eval()
+    x5, m5 = xd[:per_rank].contiguous(), md_all[:per_rank].contiguous()
+    codes5 = int(lengths[:per_rank].sum())
+
+    def quantise_and_gather():
+        with torch.no_grad():
+            return eblk.decode(eblk.encode(x5, m5))
+
+    c5_ms = timed_all(quantise_and_gather, reps=10)
+    # ---- the phoneme-conditioned quantiser at the TTS config's codebook shape (149 x 512 codes, D = 128), 16 utterances x 800 frames
+    gg = torch.Generator().manual_seed(1234 + rank)
+    g_nv, g_lb, g_n, g_t = 149, 512, 16, 800
+    g_code = torch.randn(g_nv * g_lb, EMB, generator=gg).to(dev)
+    g_x = torch.randn(g_n, EMB, g_t, generator=gg).to(dev)
+    g_tok = torch.randint(0, g_nv, (g_n, g_t), generator=gg).to(dev)
+    grouped_ms = timed_all(lambda: vqb200.assign_grouped(g_x, g_code, g_tok, g_nv, g_lb), reps=5)
+    del g_code, g_x, g_tok
+
+    times = torch.tensor([ms, e2e_s * 1e3, fwd_ms, fwd_fast_ms, fwd_graph_ms if fwd_graph_ms else 0.0, sus_ms, g_ms, c5_ms, grouped_ms],
                          dtype=torch.float64, device=dev)
-    frames = torch.tensor([float(valid_frames), float(rows), float(gjob.valid), float(gjob.rows)], dtype=torch.float64, device=dev)
+    frames = torch.tensor([float(valid_frames), float(rows), float(gjob.valid), float(gjob.rows), float(codes5)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, dist.ReduceOp.MAX)
         dist.all_reduce(frames, dist.ReduceOp.SUM)
@@ -379,7 +402,8 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms, sus_ms, g_ms = (float(times[i]) for i in range(7))
+    ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms, sus_ms, g_ms, c5_ms, grouped_ms = (float(times[i]) for i in range(9))
+    tot_codes5 = float(frames[4])
     tot_valid, tot_rows, g_tot_valid = float(frames[0]), float(frames[1]), float(frames[2])
     value = tot_valid * args.steps / (ms * 1e-3)
     e2e_value = tot_valid * args.steps / (e2e_ms * 1e-3)
@@ -529,6 +553,11 @@ def run_b200(args):
                          "encode_without_nxn_temp": cpu["encode_b8_without_nxn_temp"]},
         "index_match": {"device_path": audit, "host_path": audit_host, "gaussian": audit_gauss},
         "training_path": training,
+        "config5_quantise_plus_gather": {"value": tot_codes5 / (c5_ms * 1e-3), "unit": "codes/s", "ms": c5_ms,
+                                         "utterances_total": per_rank * world, "utterances_per_gpu": per_rank, "valid_codes_total": tot_codes5,
+                                         "api": "BottleneckBlock.encode + BottleneckBlock.decode (K1 + decode gather), inputs resident, max over ranks"},
+        "grouped_tts_quantiser": {"ms": grouped_ms, "frames_per_s_per_gpu": g_n * g_t / (grouped_ms * 1e-3), "n_vocab": g_nv, "l_bins": g_lb,
+                                  "emb_width": EMB, "frames": g_n * g_t, "api": "vq_assign_grouped (exact FP32, one warp per frame)"},
         "unsafe_rows_per_step": unsafe,
     }
     print(json.dumps(line))

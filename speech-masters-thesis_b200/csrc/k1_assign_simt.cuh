@@ -240,7 +240,10 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     __shared__ bool is_last;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // nothing the tcgen05 kernel wrote may be read before this
     const int n_list = *reinterpret_cast<volatile int*>(&hdr->unsafe_count);
-    if (n_list == 0) return;                               // common case (speech-like latents): nothing to do, nothing to re-arm
+    if (n_list == 0) {                                     // common case (speech-like latents): nothing to do, nothing to re-arm
+        if (blockIdx.x == 0 && threadIdx.x == 0) hdr->measure_residual = 0u;
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const float inf = __int_as_float(0x7f800000);
@@ -310,6 +313,7 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     if (is_last && threadIdx.x == 0) {
         hdr->unsafe_count = 0;
         hdr->list_ticket = 0;
+        hdr->measure_residual = (int64_t(n_list) * 128 > N * T) ? 1u : 0u;
     }
 }
 

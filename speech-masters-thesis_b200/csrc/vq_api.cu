@@ -178,7 +178,7 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
     const int pslot = (g_prof.on && g_prof.n < PROF_RING) ? g_prof.n++ : -1;
     prof_mark(pslot, 0, stream);
     if (!prepared) {
-        VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
+        VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, 16, stream));      // the two maxima, the worklist count and its ticket -- NOT the adaptive flag behind them
         int blocks = (w.Kp * 32 + 255) / 256;
         codebook_prepare_kernel<<<blocks, 256, 0, stream>>>(k, K, int(D), w.Kp, w.Dp, w.ee, w.hn,
                                                             w.eb, w.hdr);
@@ -475,6 +475,7 @@ vq_host_ctx* vq_host_ctx_create(int device, int64_t max_rows, int K, int D) {
         ok = ok && cudaMalloc(&c->d_x[i], size_t(c->chunk_rows) * D * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_idx[i], size_t(c->chunk_rows) * 8) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_ws[i], c->ws_bytes) == cudaSuccess;
+        ok = ok && cudaMemset(c->d_ws[i], 0, 256) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_scalars[i], VQ_NUM_SCALARS * 8) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
     }

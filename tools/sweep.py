@@ -1,6 +1,8 @@
-"""BASELINE.json configs[3]: codebook sweep K = 512 .. 65536, D = 64 .. 512 on one B200 at 262 144 frames:
-K1 time, distance-GEMM TFLOP/s against the measured tensor peak, frames sent to the exact fallback, and index
-agreement with the exact FP32 kernel on a slice.  Writes gpurun_out/sweep.json."""
+"""BASELINE.json configs[3]: codebook sweep K = 512 .. 65536 (powers of two) x D = 64 .. 512 -- the 32 grid points of
+SURVEY.md 8(d) config 4 -- on one B200 at 262 144 frames: K1 time, distance-GEMM TFLOP/s against the measured tensor
+peak, frames sent to the exact re-scan, and index agreement with the ORACLE (oracle/vq_oracle.py, chunked) on the first
+4096 rows of every point, mismatches classified in fp64.  Writes gpurun_out/sweep.json (clustered latents) or
+gpurun_out/sweep_gaussian.json (--gaussian).  --quick: the 9 corner / edge points only."""
 import ctypes
 import json
 import os
@@ -24,7 +26,7 @@ except (OSError, ValueError, KeyError):
     pass
 
 
-def run(K, D, n=128, t=2048, clustered=True, check_rows=2048):
+def run(K, D, n=128, t=2048, clustered=True, check_rows=4096):
     gen = torch.Generator(device=dev).manual_seed(K * 1000 + D)
     code = torch.randn(K, D, generator=gen, device=dev)
     if clustered:
@@ -54,11 +56,12 @@ def run(K, D, n=128, t=2048, clustered=True, check_rows=2048):
     call(sc.data_ptr())
     torch.cuda.synchronize()
     unsafe = float(sc[3])
-    # agreement with the exact kernel on the first utterances
+    # agreement with the oracle on the first utterances (fp32 matmul + min on the host, chunked; disagreements audited in fp64)
     nn = max(1, check_rows // t)
-    ref, _ = vqb200.assign(x[:nn].contiguous(), code, algo="simt")
     rows = x[:nn].permute(0, 2, 1).reshape(-1, D).cpu()
-    audit = O.audit_indices(rows, code.cpu(), ref.cpu().reshape(-1), idx[:nn].cpu().reshape(-1))
+    code_cpu = code.cpu()
+    ref, _ = O.assign_chunked(rows, code_cpu, chunk=1024 if K > 8192 else 4096)
+    audit = O.audit_indices(rows, code_cpu, ref, idx[:nn].cpu().reshape(-1))
     flops = 2.0 * n * t * K * D
     main_ms, total_ms = float(prof[1]), float(prof[0] + prof[1] + prof[2])
     return {"K": K, "D": D, "rows": n * t, "clustered": clustered, "prepare_ms": float(prof[0]), "assign_main_ms": main_ms,
@@ -69,9 +72,9 @@ def run(K, D, n=128, t=2048, clustered=True, check_rows=2048):
 
 if __name__ == "__main__":
     out = []
-    shapes = [(512, 64), (512, 128), (512, 256), (512, 512), (2048, 128), (8192, 128), (8192, 256), (65536, 64), (65536, 512)]
-    if len(sys.argv) > 1 and sys.argv[1] == "--gaussian":
-        shapes = [(512, 128), (8192, 256)]
+    shapes = [(K, D) for K in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536) for D in (64, 128, 256, 512)]
+    if "--quick" in sys.argv:
+        shapes = [(512, 64), (512, 128), (512, 256), (512, 512), (2048, 128), (8192, 128), (8192, 256), (65536, 64), (65536, 512)]
     for K, D in shapes:
         try:
             r = run(K, D, clustered="--gaussian" not in sys.argv)
