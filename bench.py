@@ -376,7 +376,7 @@ def run_b200(args):
     eblk.k, eblk.init = kd.clone(), True
     eblk.eval()
     x5, m5 = xd[:per_rank].contiguous(), md_all[:per_rank].contiguous()
-    codes5 = int(lengths[:per_rank].sum())
+    codes5 = int(job.lengths[:per_rank].sum())
 
     def quantise_and_gather():
         with torch.no_grad():

@@ -151,7 +151,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
 //   one WARP per listed frame; the frame's D values live in registers (lane = depth quad), a candidate code row is one
 //   coalesced 16-byte load per lane, eight candidates are reduced together with a transposing butterfly (9 shuffles).
 // Launched as a programmatic dependent of the tcgen05 kernel; the frame count lives in device memory.
-constexpr int L_WARPS = 4;
+constexpr int L_WARPS = 8;      // (592 blocks of 8 warps: the usual empty-worklist launch costs ~1.3 us less than 2368 blocks of 4)
 
 // One chain segment = the eight codes c = 128 nt + 16 b + res (b = 0..7) of residue chain `res` in code tile `nt`.
 // dot8 leaves in every lane the partial dot products of its depth slice with the eight codes (loads first, then FMAs).

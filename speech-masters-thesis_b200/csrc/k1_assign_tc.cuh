@@ -79,6 +79,7 @@ struct Params {
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
+    int x_cpasync;           // x tiles by cp.async (any T / alignment) instead of TMA
     int measure_mode;        // ||x - fp16(x)||: 1 measured, 0 a-priori bound, -1 adaptive (workspace header flag)
     int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
@@ -430,7 +431,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     const KeySpace ks = make_key_space(e_norm_max);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
+        for (int i = 0; i < XS; ++i) { mbar_init(smem_u32(&ctl->x_full[i]), p.x_cpasync ? 32 : 1); mbar_init(smem_u32(&ctl->x_empty[i]), 4); }
         for (int i = 0; i < B_RESIDENT_MAX; ++i) { mbar_init(smem_u32(&ctl->b_full[i]), 1); mbar_init(smem_u32(&ctl->b_empty[i]), 1); }
         for (int i = 0; i < A_BUFS_MAX; ++i) { mbar_init(smem_u32(&ctl->a_full[i]), 4); mbar_init(smem_u32(&ctl->a_empty[i]), 1); }
         for (int i = 0; i < ACC_STAGES_MAX; ++i) { mbar_init(smem_u32(&ctl->acc_full[i]), 1); mbar_init(smem_u32(&ctl->acc_empty[i]), 4); }
@@ -506,7 +507,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 const uint32_t s = q % XS, ph = (q / XS) & 1;
                 mbar_wait<500>(smem_u32(&ctl->x_empty[s]), ph ^ 1);
                 if (ch == 0) VQ_TRACE(0, it);
-                if (leader) {
+                if (p.x_cpasync) {
+                    // T % 4 != 0 or a misaligned tensor: TMA cannot describe the rows (16-byte global strides), so the whole warp
+                    // copies the [32 depth x 128 frame] box with 4-byte cp.async (zero fill outside the tensor) and every lane
+                    // arrives on the stage's barrier when its own copies have landed.
+                    const uint32_t dst0 = smem_u32(xs_base + s * X_STAGE_BYTES);
+                    const int lane_ = threadIdx.x & 31;
+                    for (int d = 0; d < XCH; ++d) {
+                        const int dd = ch * XCH + d;
+                        const float* row = p.x + (size_t(n) * p.D + size_t(min(dd, p.D - 1))) * size_t(p.T);
+#pragma unroll
+                        for (int f4 = 0; f4 < TM / 32; ++f4) {
+                            const int f = f4 * 32 + lane_, t = t0 + f;
+                            const bool ok = dd < p.D && t < p.T;
+                            const float* src = row + (ok ? t : 0);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + uint32_t(d * TM + f) * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->x_full[s])) : "memory");
+                } else if (leader) {
 #if VQ_EXPERIMENT & 32                    /* timing experiment: no x loads */
                     mbar_arrive(smem_u32(&ctl->x_full[s]));
 #else
@@ -516,6 +535,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
             }
         }
+        if (p.x_cpasync) asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp == W_BPROD) {
         // ============================================================ codebook producer
         reg_dec<REGS_ISSUER>();
@@ -1167,8 +1187,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
 // nullptr when the tcgen05 kernel takes this problem, else the reason it does not.
 inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64_t T, int K) {
     if (D > 512) return "emb_width > 512 (the FP16 A operand must fit 256 TMEM columns)";
-    if (T % 4 != 0) return "T is not a multiple of 4 (TMA needs 16-byte global strides)";
-    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return "x is not 16-byte aligned";
+    if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return "x is not 4-byte aligned";
     if (T >= (int64_t(1) << 31) || N >= (int64_t(1) << 31)) return "dimension too large for a tensor map";
     if (K > (1 << 24)) return "codebook too large";
     if (!tc::encode_tiled_fn()) return "cuTensorMapEncodeTiled is unavailable";
@@ -1190,6 +1209,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.unsafe_mask = w.unsafe_mask;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.T = int(T);
+    p.x_cpasync = (T % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) ? 1 : 0;
     p.tiles_per_utt = int((T + TM - 1) / TM);
     const int64_t n_tiles = N * p.tiles_per_utt;
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
@@ -1202,7 +1222,8 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     }
 
     CUtensorMap x_map, b_map;
-    {
+    memset(&x_map, 0, sizeof(x_map));
+    if (!p.x_cpasync) {
         cuuint64_t dims[3] = {cuuint64_t(T), cuuint64_t(D), cuuint64_t(N)};
         cuuint64_t strides[2] = {cuuint64_t(T) * 4, cuuint64_t(T) * cuuint64_t(D) * 4};
         cuuint32_t box[3] = {TM, XCH, 1};

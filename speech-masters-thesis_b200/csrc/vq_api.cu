@@ -194,7 +194,7 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         // Programmatic dependent launch: the kernel is set up while the main kernel still runs (which signals
         // launch_dependents right after its prologue) and waits on griddepcontrol.wait before it reads the count, so the
         // usual empty-worklist case costs ~3 us less than a serialised launch.
-        const int gx = int(std::min<int64_t>(16 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
+        const int gx = int(std::min<int64_t>(4 * int64_t(num_sms()), (N * T + L_WARPS - 1) / L_WARPS));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx);
         cfg.blockDim = dim3(L_WARPS * 32);

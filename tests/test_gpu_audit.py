@@ -83,6 +83,31 @@ def test_sweep_corner_against_oracle(vq, corner, clustered):
         audit(x, code, idx, chunk=1024 if K > 8192 else 8192)
 
 
+@pytest.mark.parametrize("shape", [(6, 128, 1733, 512), (3, 128, 131, 512), (2, 64, 1001, 1024), (1, 256, 37, 8192), (4, 128, 2, 512)],
+                         ids=lambda s: f"N{s[0]}_D{s[1]}_T{s[2]}_K{s[3]}")
+@pytest.mark.parametrize("clustered", [True, False], ids=["clustered", "gaussian"])
+def test_tcgen05_route_for_t_not_a_multiple_of_4(vq, shape, clustered):
+    """T % 4 != 0 (VQTTS / vqlatent crops) used to drop the whole call to the CUDA-core kernel (TMA needs 16-byte global
+    strides); the tcgen05 kernel now loads such tensors with cp.async.  algo='tc' must accept them and stay exact; a misaligned
+    view (offset by one float) takes the same route."""
+    n, D, t, K = shape
+    gen = torch.Generator().manual_seed(t * 7 + K)
+    code = torch.randn(K, D, generator=gen)
+    lengths = torch.randint(max(1, t // 2), t + 1, (n,), generator=gen)
+    lengths[0] = t
+    x, _ = O.synthetic_batch(lengths, D, gen, codebook=code if clustered else None)
+    idx, _ = vq.assign(x.to(DEV), code.to(DEV), algo="tc")
+    audit(x, code, idx)
+    if t % 4 == 1:                                            # an aligned T with a misaligned base pointer
+        flat = torch.empty(n * D * (t + 3) + 1, device=DEV)
+        view = flat[1:1 + n * D * (t + 3)].view(n, D, t + 3)
+        xp = torch.nn.functional.pad(x, (0, 3))
+        view.copy_(xp.to(DEV))
+        assert view.data_ptr() % 16 != 0
+        idx2, _ = vq.assign(view, code.to(DEV), algo="tc")
+        audit(xp, code, idx2)
+
+
 def test_second_device_gets_its_shared_memory_opt_in(vq):
     """cudaFuncSetAttribute is per device: the same process must be able to run the kernels on cuda:1 after cuda:0."""
     if torch.cuda.device_count() < 2:
