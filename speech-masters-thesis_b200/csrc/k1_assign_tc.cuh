@@ -39,6 +39,9 @@
 #include "k1_prepare.cuh"
 #include "vq_common.cuh"
 
+#ifndef VQ_AB
+#define VQ_AB 0              // A/B bisection builds (tools/ab_k1.py): 1 no chain flags in the scan, 2 no mask in finish, 4 groups by qa parity, 8 no pipelined issue loop
+#endif
 #ifndef VQ_EXPERIMENT
 #define VQ_EXPERIMENT 0      // timing experiments (tools/experiment.sh); results are wrong by construction when != 0
 #endif
@@ -605,7 +608,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
 #if !(VQ_EXPERIMENT & (16 | 64 | 128))
-                if (resident && !pair && it != 0 && p.pipe_issue && (n_kb == 1 || n_kb == 2 || n_kb == 4)) {
+                if (!(VQ_AB & 8) && resident && !pair && it != 0 && p.pipe_issue && (n_kb == 1 || n_kb == 2 || n_kb == 4)) {
                     // Software-pipelined steady state (N = 128 batches).  The tensor core's queue is only a couple of
                     // instructions deep, so the ~40 scalar instructions between two batches (barrier probe, ring arithmetic,
                     // descriptors; ~200 cycles on this single warp, ~650 at a tile boundary) were bubbles in the tensor pipe.
@@ -875,7 +878,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 const bool keys_ok = in_range && (!p.fold || fold_ok);
                 safe = safe && keys_ok && c1 < p.K;
-                if (!safe && keys_ok) {
+                if (!(VQ_AB & 2) && !safe && keys_ok) {
                     // Pruning for the exact re-scan: a code c can only be the exact winner if its approximate score is within
                     // 2 err of the approximate best (s16(c) >= s(c) - err >= s(best) - err >= s16(best) - 2 err); each scan
                     // group flagged the residue chains whose maximum clears its own (lower or equal) threshold, and a group
@@ -991,7 +994,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa, rs.next(acc_stages)) {
                 // The two scan groups take ALTERNATE code tiles (group 0 the even ones), so one group's TMEM loads and barrier
                 // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
-                if ((uint32_t(nt) & 1u) != uint32_t(wg)) continue;
+                if ((((VQ_AB & 4) ? qa : uint32_t(nt)) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
                 // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
                 // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
@@ -1053,7 +1056,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             // unsafe): normally only the best's own chain; when the group's runner-up is within 2 err of its best, every chain
             // whose maximum is.  (rowstat of this tile was written by the front group before the tile's MMAs were issued.)
             uint32_t chains = 1u << res;
-            if (r1 - r2 <= gap_cap) {                              // (keys are the raw bits of floats in one binade: a difference in ulps)
+            if (!(VQ_AB & 1) && ((VQ_AB & 16) ? __any_sync(0xffffffffu, r1 - r2 <= gap_cap) != 0 : (r1 - r2 <= gap_cap))) {   // (keys are the raw bits of floats in one binade: a difference in ulps)
                 // 2 err <= err_c[0] ||x||^2 + err_c[1]: an a-priori bound (looser than finish()'s measured err, so the flagged
                 // set is a superset of what the proof needs) that costs one FMA here instead of two square roots
                 const float reach = __uint_as_float(r1) - fmaf(ctl->err_c[0], rowstat[cb * TM + r].x, ctl->err_c[1]);
