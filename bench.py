@@ -334,7 +334,10 @@ def run_b200(args):
 
     md_all = mask.to(dev)
     blk = vqb200.BottleneckBlock(K_BINS, EMB, 0.99, 1.0).to(dev)
-    blk.k, blk.k_sum, blk.k_elem, blk.init = kd.clone(), kd.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
+    k0 = kd.clone()
+    if world > 1:
+        dist.broadcast(k0, 0)                 # one codebook for all replicas (every rank's synthetic batch has its own)
+    blk.k, blk.k_sum, blk.k_elem, blk.init = k0, k0.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
     blk.train()
     fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
     blk.rng_parity = False                   # restart rows drawn on the device: no host sync, no CPU randperm

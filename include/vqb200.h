@@ -73,9 +73,7 @@ const char* vq_last_error(void);
 /* 1 when the current device can run the tcgen05 kernels (compute capability 10.x), else 0. */
 int         vq_device_supported(void);
 
-/* Bytes of scratch vq_assign needs for this shape (FP16 codebook image, norms, fallback worklist).  Zero the first 256
- * bytes once after allocating it: the header keeps one adaptive flag across calls (whether the previous call re-scanned
- * enough frames for the tighter, costlier error measurement to pay) -- results never depend on it, only the speed does. */
+/* Bytes of scratch vq_assign needs for this shape (FP16 codebook image, norms, fallback worklist). */
 size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_width);
 
 /* K1 -- replaces BottleneckBlock.preprocess + quantize (bottleneck.py:92-100,126-141) and, for the

@@ -235,13 +235,13 @@ __global__ void __launch_bounds__(L_WARPS * 32)
 assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
                    const float* __restrict__ ee, int K, int n_code_tiles, int64_t* __restrict__ idx, float* __restrict__ min_d,
                    double* __restrict__ scalars, const int* __restrict__ row_list, const uint32_t* __restrict__ row_mask,
-                   AssignHeader* __restrict__ hdr) {
+                   AssignHeader* __restrict__ hdr, unsigned int* hard_hint) {
     __shared__ double red[32];
     __shared__ bool is_last;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // nothing the tcgen05 kernel wrote may be read before this
     const int n_list = *reinterpret_cast<volatile int*>(&hdr->unsafe_count);
     if (n_list == 0) {                                     // common case (speech-like latents): nothing to do, nothing to re-arm
-        if (blockIdx.x == 0 && threadIdx.x == 0) hdr->measure_residual = 0u;
+        if (hard_hint && blockIdx.x == 0 && threadIdx.x == 0) *hard_hint = 0u;
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,7 +313,10 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     if (is_last && threadIdx.x == 0) {
         hdr->unsafe_count = 0;
         hdr->list_ticket = 0;
-        hdr->measure_residual = (int64_t(n_list) * 128 > N * T) ? 1u : 0u;
+        if (hard_hint) {                       // mapped host memory: which kernel variant the host launches next (see hard_hint())
+            *hard_hint = (int64_t(n_list) * 128 > N * T) ? 1u : 0u;
+            __threadfence_system();
+        }
     }
 }
 

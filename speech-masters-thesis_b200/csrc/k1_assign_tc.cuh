@@ -39,9 +39,6 @@
 #include "k1_prepare.cuh"
 #include "vq_common.cuh"
 
-#ifndef VQ_AB
-#define VQ_AB 0              // A/B bisection builds (tools/ab_k1.py): 1 no chain flags in the scan, 2 no mask in finish, 4 groups by qa parity, 8 no pipelined issue loop
-#endif
 #ifndef VQ_EXPERIMENT
 #define VQ_EXPERIMENT 0      // timing experiments (tools/experiment.sh); results are wrong by construction when != 0
 #endif
@@ -83,7 +80,6 @@ struct Params {
     int a_const_col;         // TMEM column of the constant [1,1,1,0,...] A slice used by the folded k-step
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
     int x_cpasync;           // x tiles by cp.async (any T / alignment) instead of TMA
-    int measure_mode;        // ||x - fp16(x)||: 1 measured, 0 a-priori bound, -1 adaptive (workspace header flag)
     int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
@@ -414,7 +410,13 @@ inline size_t handoff_bytes(int cd) { return size_t(cd) * (2 * TM * sizeof(Cand)
 
 // RESCORE = true additionally re-scores the shortlisted code in exact FP32 (needed for min_d / sum(min_d) and for
 // the audit output; it also halves the safety margin); RESCORE = false decides from the approximate scores alone.
-template <bool RESCORE>
+// HARD = true is the variant for adversarial batches (many near-ties): it MEASURES ||x - fp16(x)|| per frame (1.6x fewer frames
+// fail the safety test than with the a-priori bound 2^-11 ||x||) and flags, per unsafe frame, the residue chains the exact
+// re-scan has to visit.  Both cost time on every frame (7 of the 11 front-group instructions per depth pair; the flagging code
+// in the scan groups costs ~5 % just by being there), and speech-like batches never need them: HARD = false bounds the residual
+// a priori and lets the rare unsafe frame be re-scanned over all codes.  The host picks the variant from a hint the re-scan
+// kernel leaves in mapped host memory (see hard_hint() below).
+template <bool RESCORE, bool HARD>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -608,7 +610,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 VQ_TRACE(1, it);
                 const uint32_t a_tmem = tmem + a_col0 + a * a_stride;
 #if !(VQ_EXPERIMENT & (16 | 64 | 128))
-                if (!(VQ_AB & 8) && resident && !pair && it != 0 && p.pipe_issue && (n_kb == 1 || n_kb == 2 || n_kb == 4)) {
+                if (resident && !pair && it != 0 && p.pipe_issue && (n_kb == 1 || n_kb == 2 || n_kb == 4)) {
                     // Software-pipelined steady state (N = 128 batches).  The tensor core's queue is only a couple of
                     // instructions deep, so the ~40 scalar instructions between two batches (barrier probe, ring arithmetic,
                     // descriptors; ~200 cycles on this single warp, ~650 at a tile boundary) were bubbles in the tensor pipe.
@@ -878,7 +880,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 const bool keys_ok = in_range && (!p.fold || fold_ok);
                 safe = safe && keys_ok && c1 < p.K;
-                if (!(VQ_AB & 2) && !safe && keys_ok) {
+                if (HARD && !safe && keys_ok) {
                     // Pruning for the exact re-scan: a code c can only be the exact winner if its approximate score is within
                     // 2 err of the approximate best (s16(c) >= s(c) - err >= s(best) - err >= s16(best) - 2 err); each scan
                     // group flagged the residue chains whose maximum clears its own (lower or equal) threshold, and a group
@@ -914,11 +916,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             }
         };
 
-        // ||x - fp16(x)|| per frame: MEASURED (7 of the 11 instructions per depth pair of this loop, ~7 % of the kernel) or bounded a
-        // priori by 2^-11 ||x|| (2.4x looser: 1.6x more frames fail the safety test on adversarial i.i.d. latents, none on
-        // speech-like ones).  The workspace header remembers whether the previous call on this workspace re-scanned more than
-        // ~0.8 % of its frames (set by the re-scan kernel); only then is the measurement worth its cost.
-        const bool measure = p.measure_mode == 1 || (p.measure_mode < 0 && p.hdr->measure_residual != 0);
+        // ||x - fp16(x)|| per frame: MEASURED (HARD: 7 of the 11 instructions per depth pair of this loop, ~7 % of the kernel) or
+        // bounded a priori by 2^-11 ||x|| (2.4x looser: 1.6x more frames fail the safety test on adversarial i.i.d. latents, none
+        // on speech-like ones).
+        constexpr bool measure = HARD;
         Ring ra, rstat;                                       // A buffer being filled; row-statistics slot of this tile
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, ra.next(uint32_t(p.a_bufs)), rstat.next(uint32_t(p.cd))) {
             const uint32_t a = ra.i, aph = ra.ph;
@@ -984,7 +985,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         Ring rc;                                              // hand-off slot of this tile
         Ring rs;                                              // accumulator stage of code tile qa (2 or 3 stages)
         const uint32_t acc_stages = uint32_t(p.acc_stages);
-        const uint32_t gap_cap = ctl->gap_cap;                 // best - runner-up above this many ulps: safe whatever the frame's norm
+        const uint32_t gap_cap = HARD ? ctl->gap_cap : 0u;     // best - runner-up above this many ulps: safe whatever the frame's norm
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, rc.next(uint32_t(p.cd))) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
@@ -994,7 +995,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa, rs.next(acc_stages)) {
                 // The two scan groups take ALTERNATE code tiles (group 0 the even ones), so one group's TMEM loads and barrier
                 // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
-                if ((((VQ_AB & 4) ? qa : uint32_t(nt)) & 1u) != uint32_t(wg)) continue;
+                if ((uint32_t(nt) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
                 // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
                 // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
@@ -1056,7 +1057,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             // unsafe): normally only the best's own chain; when the group's runner-up is within 2 err of its best, every chain
             // whose maximum is.  (rowstat of this tile was written by the front group before the tile's MMAs were issued.)
             uint32_t chains = 1u << res;
-            if (!(VQ_AB & 1) && ((VQ_AB & 16) ? __any_sync(0xffffffffu, r1 - r2 <= gap_cap) != 0 : (r1 - r2 <= gap_cap))) {   // (keys are the raw bits of floats in one binade: a difference in ulps)
+            if (HARD && r1 - r2 <= gap_cap) {                      // (keys are the raw bits of floats in one binade: a difference in ulps)
                 // 2 err <= err_c[0] ||x||^2 + err_c[1]: an a-priori bound (looser than finish()'s measured err, so the flagged
                 // set is a superset of what the proof needs) that costs one FMA here instead of two square roots
                 const float reach = __uint_as_float(r1) - fmaf(ctl->err_c[0], rowstat[cb * TM + r].x, ctl->err_c[1]);
@@ -1113,7 +1114,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
 // VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, measure = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, hard = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
@@ -1121,7 +1122,7 @@ struct TcEnv {
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
         if (const char* e = getenv("VQ_K1_PIPE")) pipe = atoi(e);
         if (const char* e = getenv("VQ_K1_AWAIT")) await = atoi(e);
-        if (const char* e = getenv("VQ_K1_MEASURE")) measure = atoi(e);
+        if (const char* e = getenv("VQ_K1_HARD")) hard = atoi(e);
     }
 };
 inline const TcEnv& tc_env() {
@@ -1174,7 +1175,6 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
     p.await_mode = tc_env().await >= 0 ? tc_env().await : 0;
-    p.measure_mode = tc_env().measure;                           // VQ_K1_MEASURE=0 / 1 forces a mode (A/B switch); default adaptive
     p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns
@@ -1185,6 +1185,25 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
            (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES + (p.const_smem ? ACONST_BYTES : 0) : (p.hn_in_smem ? size_t(Kp) * 4 : 0));
     if (smem > budget) return "shared memory budget exceeded";
     return nullptr;
+}
+
+// "Hard batch" hint, one word per device in mapped, pinned host memory: the re-scan kernel writes 1 there when it had to
+// re-scan more than 1/128 of a call's frames and 0 when it had (almost) nothing to do; the host reads it -- without any
+// synchronisation, so it lags by a call or two -- to pick the kernel variant of the NEXT call.  A wrong guess only costs time.
+inline unsigned int* hard_hint(int device) {
+    static unsigned int* page = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!page) {
+        void* ptr = nullptr;
+        if (cudaHostAlloc(&ptr, 64 * sizeof(unsigned int), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        page = static_cast<unsigned int*>(ptr);
+        for (int i = 0; i < 64; ++i) page[i] = 0u;
+    }
+    return (device >= 0 && device < 64) ? page + device : nullptr;
 }
 
 // nullptr when the tcgen05 kernel takes this problem, else the reason it does not.
@@ -1246,12 +1265,24 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(codebook) failed with CUresult %s%lld", "", (long long)r);
     }
-    VQ_CUDA_OK(ensure_dynamic_smem(assign_tc_kernel<true>, 227 * 1024));
-    VQ_CUDA_OK(ensure_dynamic_smem(assign_tc_kernel<false>, 227 * 1024));
+    int dev = 0;
+    VQ_CUDA_OK(cudaGetDevice(&dev));
+    const unsigned int* hint = hard_hint(dev);
+    bool hard = hint && *reinterpret_cast<const volatile unsigned int*>(hint) != 0u;
+    if (tc_env().hard >= 0) hard = tc_env().hard != 0;              // VQ_K1_HARD=0 / 1 forces a variant (A/B switch)
+    if (dbg) hard = true;                                           // the audit entry point reports the measured bound
     const int grid = int(std::min<int64_t>(n_tiles, num_sms()));
     const bool rescore = force_rescore >= 0 ? force_rescore != 0 : (min_d || scalars || dbg);
-    if (rescore) assign_tc_kernel<true><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
-    else assign_tc_kernel<false><<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = ensure_dynamic_smem(kernel, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
+        return cudaGetLastError();
+    };
+    if (rescore && hard) VQ_CUDA_OK(launch(assign_tc_kernel<true, true>));
+    else if (rescore) VQ_CUDA_OK(launch(assign_tc_kernel<true, false>));
+    else if (hard) VQ_CUDA_OK(launch(assign_tc_kernel<false, true>));
+    else VQ_CUDA_OK(launch(assign_tc_kernel<false, false>));
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -13,9 +13,7 @@ struct AssignHeader {
     unsigned int e_err_max_bits;    // max_c ||e_c - fp16(e_c)||
     int unsafe_count;               // rows queued for the exact fallback (reset by the fallback kernel's last block)
     unsigned int list_ticket;       // last-block ticket of the fallback kernel
-    unsigned int measure_residual;  // set by the re-scan kernel when the previous call re-scanned > 1/128 of its frames: the next call then
-                                    // measures ||x - fp16(x)|| per frame instead of bounding it a priori (fewer re-scans, 7 % more work)
-    int pad[59];
+    int pad[60];
 };
 static_assert(sizeof(AssignHeader) == 256, "header is 256 bytes");
 

@@ -178,7 +178,7 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
     const int pslot = (g_prof.on && g_prof.n < PROF_RING) ? g_prof.n++ : -1;
     prof_mark(pslot, 0, stream);
     if (!prepared) {
-        VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, 16, stream));      // the two maxima, the worklist count and its ticket -- NOT the adaptive flag behind them
+        VQ_CUDA_OK(cudaMemsetAsync(w.hdr, 0, sizeof(AssignHeader), stream));
         int blocks = (w.Kp * 32 + 255) / 256;
         codebook_prepare_kernel<<<blocks, 256, 0, stream>>>(k, K, int(D), w.Kp, w.Dp, w.ee, w.hn,
                                                             w.eb, w.hdr);
@@ -206,9 +206,12 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
         cfg.numAttrs = (g_prof.on && pslot >= 0) ? 0 : 1;          // (event records between the two kernels serialise them anyway)
         const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
         const int n_code_tiles = w.Kp / 128;
+        int dev = 0;
+        VQ_CUDA_OK(cudaGetDevice(&dev));
+        unsigned int* hint_dev = hard_hint(dev);               // (unified addressing: the mapped host pointer is valid on the device)
         auto launch_list = [&](auto kernel) {
             return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d, scalars,
-                                      (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr);
+                                      (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr, hint_dev);
         };
         if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1>));
         else if (vec) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 4>));
@@ -475,7 +478,6 @@ vq_host_ctx* vq_host_ctx_create(int device, int64_t max_rows, int K, int D) {
         ok = ok && cudaMalloc(&c->d_x[i], size_t(c->chunk_rows) * D * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_idx[i], size_t(c->chunk_rows) * 8) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_ws[i], c->ws_bytes) == cudaSuccess;
-        ok = ok && cudaMemset(c->d_ws[i], 0, 256) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_scalars[i], VQ_NUM_SCALARS * 8) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
     }

@@ -53,7 +53,7 @@ class _Workspace:
         key = cls._key(device)
         buf = cls._cache.get(key)
         if buf is None or buf.numel() < need:
-            buf = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)     # (zeroed: the header keeps an adaptive flag)
+            buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
             cls._cache[key] = buf
             cls._prepared.pop(key, None)
         return buf
