@@ -89,6 +89,16 @@ int vq_assign(const float* x, int64_t n_utt, int64_t emb_width, int64_t t_frames
               int64_t* idx, float* min_d, double* scalars,
               void* workspace, size_t workspace_bytes, int algo, void* stream);
 
+/* vq_assign for BF16 latents (bf16 autocast training / inference: the encoder hands over [N,D,T] bfloat16, T contiguous).
+ * Same outputs and the same exactness contract as vq_assign on x.float() -- BF16 -> FP16 is exact in the normal range, and
+ * any frame that is not provably safe is re-scanned from the BF16 values in FP32 -- without the extra pass that an up-cast
+ * would cost (6D bytes per frame).  The tcgen05 path needs T % 8 == 0 and a 16-byte aligned tensor; other shapes take the
+ * exact CUDA-core kernel. */
+int vq_assign_bf16(const void* x_bf16, int64_t n_utt, int64_t emb_width, int64_t t_frames,
+                   const float* k, int k_bins,
+                   int64_t* idx, float* min_d, double* scalars,
+                   void* workspace, size_t workspace_bytes, int algo, void* stream);
+
 /* Grouped (phoneme-conditioned) K1 -- replaces the per-frame codebook gather + bmm + min of the TTS quantiser
  * (models/vqtts/bottleneck.py:38-58): the codebook k is [n_vocab * l_bins, D]; frame j only competes among the l_bins
  * codes of its token tok[j] (int64 [N*T], the aligned token ids of :28; values are clamped to [0, n_vocab)).

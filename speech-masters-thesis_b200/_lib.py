@@ -31,6 +31,8 @@ SIGNATURES = {
     "vq_workspace_bytes": (_c_size_t, [_c_i64, _c_i64, _c_int, _c_int]),
     "vq_assign": (_c_int, [_c_void_p, _c_i64, _c_i64, _c_i64, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "vq_assign_bf16": (_c_int, [_c_void_p, _c_i64, _c_i64, _c_i64, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "vq_assign_grouped": (_c_int, [_c_void_p, _c_i64, _c_i64, _c_i64, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                    _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "vq_assign_debug": (_c_int, [_c_void_p, _c_i64, _c_i64, _c_i64, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p,

@@ -15,8 +15,9 @@ constexpr int S_BN = 64;    // codes per inner tile
 constexpr int S_BK = 16;    // depth per step
 
 // Tile i covers frames [t0, t0+128) of utterance n (tiles never straddle utterances).
+template <typename XT>
 __global__ void __launch_bounds__(256)
-assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
+assign_simt_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T,
                    const float* __restrict__ k, const float* __restrict__ ee, int K,
                    int64_t* __restrict__ idx, float* __restrict__ min_d, double* __restrict__ scalars) {
     __shared__ __align__(16) float Xs[S_BK][S_BM];
@@ -61,7 +62,7 @@ assign_simt_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T,
                     int kk = (tid >> 7) + 2 * i, r = tid & 127;
                     long long off = row_off[r];
                     float v = 0.f;
-                    if (off >= 0 && d0 + kk < D) v = x[off + int64_t(d0 + kk) * T];
+                    if (off >= 0 && d0 + kk < D) v = x_to_float(x[off + int64_t(d0 + kk) * T]);
                     Xs[kk][r] = v;
                 }
                 // ---- stage E: 64 codes x 16 depth, transposed into [depth][code]
@@ -230,9 +231,9 @@ struct ListWalk {
 // The per-frame work is a chain of dependent L2 / DRAM round trips (frame id -> x -> code rows -> ||e||^2), so the kernel is
 // latency-bound: two segments are evaluated per step (16 code rows and both norms in flight at once) and frames are spread
 // one per warp over as many resident warps as the register budget allows (MAXQ = 1 for D <= 128).
-template <bool VEC, int MAXQ>
+template <bool VEC, int MAXQ, typename XT>
 __global__ void __launch_bounds__(L_WARPS * 32)
-assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
+assign_list_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
                    const float* __restrict__ ee, int K, int n_code_tiles, int64_t* __restrict__ idx, float* __restrict__ min_d,
                    double* __restrict__ scalars, const int* __restrict__ row_list, const uint32_t* __restrict__ row_mask,
                    AssignHeader* __restrict__ hdr, unsigned int* hard_hint) {
@@ -251,7 +252,7 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
     for (int j = blockIdx.x * L_WARPS + warp; j < n_list; j += gridDim.x * L_WARPS) {
         const int64_t row = row_list[j];
         const uint32_t mask = row_mask[j];
-        const float* src = x + (row / T) * int64_t(D) * T + (row % T);
+        const XT* src = x + (row / T) * int64_t(D) * T + (row % T);
         // this lane's slice of the frame: depths 4 (lane + 32 q) .. + 3   (VEC)   or   lane + 32 i   (scalar)
         float xr[4 * MAXQ];
         float xx = 0.f;
@@ -260,7 +261,7 @@ assign_list_kernel(const float* __restrict__ x, int64_t N, int D, int64_t T, con
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int d = VEC ? 4 * (lane + 32 * q) + u : lane + 32 * (4 * q + u);
-                const float v = d < D ? __ldg(src + int64_t(d) * T) : 0.f;
+                const float v = d < D ? x_to_float(__ldg(src + int64_t(d) * T)) : 0.f;
                 xr[4 * q + u] = v;
                 xx = fmaf(v, v, xx);
             }

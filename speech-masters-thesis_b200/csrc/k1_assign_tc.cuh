@@ -67,7 +67,7 @@ constexpr uint32_t WAIT_HINT_NS = 2000;
 constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared memory up to this many (padded) codes
 
 struct Params {
-    const float* x; const float* k; const float* ee; const float* hn; const float* hn_off;
+    const void* x; const float* k; const float* ee; const float* hn; const float* hn_off;
     AssignHeader* hdr; int* unsafe_rows; uint32_t* unsafe_mask;
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
@@ -416,7 +416,7 @@ inline size_t handoff_bytes(int cd) { return size_t(cd) * (2 * TM * sizeof(Cand)
 // in the scan groups costs ~5 % just by being there), and speech-like batches never need them: HARD = false bounds the residual
 // a priori and lets the rare unsafe frame be re-scanned over all codes.  The host picks the variant from a hint the re-scan
 // kernel leaves in mapped host memory (see hard_hint() below).
-template <bool RESCORE, bool HARD>
+template <bool RESCORE, bool HARD, typename XT>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -521,7 +521,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     const int lane_ = threadIdx.x & 31;
                     for (int d = 0; d < XCH; ++d) {
                         const int dd = ch * XCH + d;
-                        const float* row = p.x + (size_t(n) * p.D + size_t(min(dd, p.D - 1))) * size_t(p.T);
+                        const float* row = static_cast<const float*>(p.x) + (size_t(n) * p.D + size_t(min(dd, p.D - 1))) * size_t(p.T);   // (FP32 latents only)
 #pragma unroll
                         for (int f4 = 0; f4 < TM / 32; ++f4) {
                             const int f = f4 * 32 + lane_, t = t0 + f;
@@ -535,7 +535,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #if VQ_EXPERIMENT & 32                    /* timing experiment: no x loads */
                     mbar_arrive(smem_u32(&ctl->x_full[s]));
 #else
-                    mbar_expect_tx(smem_u32(&ctl->x_full[s]), X_STAGE_BYTES);
+                    mbar_expect_tx(smem_u32(&ctl->x_full[s]), XCH * TM * int(sizeof(XT)));     // (BF16 boxes fill half a stage)
                     tma_load_3d(smem_u32(xs_base + s * X_STAGE_BYTES), &x_map, smem_u32(&ctl->x_full[s]), t0, ch * XCH, n);
 #endif
                 }
@@ -853,14 +853,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 float dot = 0.f;
                 if (RESCORE) {
                     const int cs = min(c1, p.K - 1);
-                    const float* xr = p.x + (size_t(n) * p.D) * p.T + t;
+                    const XT* xr = static_cast<const XT*>(p.x) + (size_t(n) * p.D) * p.T + t;
                     const float* er = p.k + size_t(cs) * p.D;
                     int d = 0;
                     if (p.vec_k) {
                         for (; d + 16 <= p.D; d += 16) {            // 16 independent loads in flight per thread
                             float xv[16];
 #pragma unroll
-                            for (int u = 0; u < 16; ++u) xv[u] = __ldg(xr + size_t(d + u) * p.T);
+                            for (int u = 0; u < 16; ++u) xv[u] = x_to_float(__ldg(xr + size_t(d + u) * p.T));
 #pragma unroll
                             for (int u4 = 0; u4 < 4; ++u4) {
                                 const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d + 4 * u4));
@@ -871,7 +871,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                         }
                     }
-                    for (; d < p.D; ++d) dot = fmaf(__ldg(xr + size_t(d) * p.T), __ldg(er + d), dot);
+                    for (; d < p.D; ++d) dot = fmaf(x_to_float(__ldg(xr + size_t(d) * p.T)), __ldg(er + d), dot);
                     const float g1 = dot - p.hn[cs];
                     const float s_bound = t_bound - ks.offset;      // exact: t and B share an exponent
                     // c1 is the exact argmax if its exact score clears every other code's approximate score + its error
@@ -937,7 +937,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 const uint32_t s = qx % XS, ph = (qx / XS) & 1;
                 mbar_wait<64>(smem_u32(&ctl->x_full[s]), ph);
                 if (wq == 0 && ch == 0) VQ_TRACE(4, it);
-                const float* xs = reinterpret_cast<const float*>(xs_base + s * X_STAGE_BYTES) + r;
+                const XT* xs = reinterpret_cast<const XT*>(xs_base + s * X_STAGE_BYTES) + r;
                 uint32_t pk[16];
 #if VQ_EXPERIMENT & 8                     /* timing experiment: no conversion work */
 #pragma unroll
@@ -947,7 +947,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 if (measure) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float v0 = xs[(2 * j) * TM], v1 = xs[(2 * j + 1) * TM];
+                        const float v0 = x_to_float(xs[(2 * j) * TM]), v1 = x_to_float(xs[(2 * j + 1) * TM]);
                         const __half2 h = __floats2half2_rn(v0, v1);          // low half = even depth, high half = odd depth
                         xa[(2 * j) & 3] = fmaf(v0, v0, xa[(2 * j) & 3]); xa[(2 * j + 1) & 3] = fmaf(v1, v1, xa[(2 * j + 1) & 3]);
                         const float2 f = __half22float2(h);
@@ -958,7 +958,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float v0 = xs[(2 * j) * TM], v1 = xs[(2 * j + 1) * TM];
+                        const float v0 = x_to_float(xs[(2 * j) * TM]), v1 = x_to_float(xs[(2 * j + 1) * TM]);
                         const __half2 h = __floats2half2_rn(v0, v1);
                         xa[(2 * j) & 3] = fmaf(v0, v0, xa[(2 * j) & 3]); xa[(2 * j + 1) & 3] = fmaf(v1, v1, xa[(2 * j + 1) & 3]);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -1214,9 +1214,11 @@ inline unsigned int* hard_hint(int device) {
 }
 
 // nullptr when the tcgen05 kernel takes this problem, else the reason it does not.
-inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64_t T, int K) {
+inline const char* tc_unsupported_reason(const void* x, int64_t N, int D, int64_t T, int K, int x_elem_bytes = 4) {
     if (D > 512) return "emb_width > 512 (the FP16 A operand must fit 256 TMEM columns)";
-    if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return "x is not 4-byte aligned";
+    if (x_elem_bytes == 4 && (reinterpret_cast<uintptr_t>(x) & 3) != 0) return "x is not 4-byte aligned";
+    if (x_elem_bytes == 2 && (T % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0))
+        return "BF16 latents need T % 8 == 0 and a 16-byte aligned tensor (TMA strides)";
     if (T >= (int64_t(1) << 31) || N >= (int64_t(1) << 31)) return "dimension too large for a tensor map";
     if (K > (1 << 24)) return "codebook too large";
     if (!tc::encode_tiled_fn()) return "cuTensorMapEncodeTiled is unavailable";
@@ -1225,7 +1227,8 @@ inline const char* tc_unsupported_reason(const float* x, int64_t N, int D, int64
     return plan_assign_tc(D, K, p, smem);
 }
 
-inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const float* k, int K, int64_t* idx, float* min_d,
+template <typename XT>
+inline int launch_assign_tc(const XT* x, int64_t N, int D, int64_t T, const float* k, int K, int64_t* idx, float* min_d,
                             double* scalars, const AssignWorkspace& w, cudaStream_t stream, float* dbg = nullptr,
                             long long* trace = nullptr, int trace_tiles = 0, int force_rescore = -1) {
     using namespace tc;
@@ -1238,7 +1241,7 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.unsafe_mask = w.unsafe_mask;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.T = int(T);
-    p.x_cpasync = (T % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) ? 1 : 0;
+    p.x_cpasync = (sizeof(XT) == 4 && (T % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)) ? 1 : 0;
     p.tiles_per_utt = int((T + TM - 1) / TM);
     const int64_t n_tiles = N * p.tiles_per_utt;
     VQ_REQUIRE(n_tiles < (int64_t(1) << 31), "too many tiles");
@@ -1254,10 +1257,10 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
     memset(&x_map, 0, sizeof(x_map));
     if (!p.x_cpasync) {
         cuuint64_t dims[3] = {cuuint64_t(T), cuuint64_t(D), cuuint64_t(N)};
-        cuuint64_t strides[2] = {cuuint64_t(T) * 4, cuuint64_t(T) * cuuint64_t(D) * 4};
+        cuuint64_t strides[2] = {cuuint64_t(T) * sizeof(XT), cuuint64_t(T) * cuuint64_t(D) * sizeof(XT)};
         cuuint32_t box[3] = {TM, XCH, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = encode(&x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, es,
+        CUresult r = encode(&x_map, sizeof(XT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<XT*>(x), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(x) failed with CUresult %s%lld", "", (long long)r);
@@ -1286,10 +1289,10 @@ inline int launch_assign_tc(const float* x, int64_t N, int D, int64_t T, const f
         kernel<<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
         return cudaGetLastError();
     };
-    if (rescore && hard) VQ_CUDA_OK(launch(assign_tc_kernel<true, true>));
-    else if (rescore) VQ_CUDA_OK(launch(assign_tc_kernel<true, false>));
-    else if (hard) VQ_CUDA_OK(launch(assign_tc_kernel<false, true>));
-    else VQ_CUDA_OK(launch(assign_tc_kernel<false, false>));
+    if (rescore && hard) VQ_CUDA_OK(launch(assign_tc_kernel<true, true, XT>));
+    else if (rescore) VQ_CUDA_OK(launch(assign_tc_kernel<true, false, XT>));
+    else if (hard) VQ_CUDA_OK(launch(assign_tc_kernel<false, true, XT>));
+    else VQ_CUDA_OK(launch(assign_tc_kernel<false, false, XT>));
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -150,7 +150,9 @@ size_t vq_workspace_bytes(int64_t n_utt, int64_t t_frames, int k_bins, int emb_w
     return w.bytes + 256;
 }
 
-static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
+extern "C++" {
+template <typename XT>
+static int assign_impl(const XT* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
                        int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
                        int algo, void* stream_, float* dbg, long long* trace = nullptr, int trace_tiles = 0) {
     if (check_shape(N, D, T, K)) return 1;
@@ -166,11 +168,11 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
     algo &= ~VQ_ALGO_PREPARED;
     bool use_tc = false;
     if (algo == VQ_ALGO_TC) {
-        const char* why = tc_unsupported_reason(x, N, int(D), T, K);
+        const char* why = tc_unsupported_reason(x, N, int(D), T, K, int(sizeof(XT)));
         if (why) return fail("vq_assign: VQ_ALGO_TC requested but %s", why);
         use_tc = true;
     } else if (algo == VQ_ALGO_AUTO) {
-        use_tc = tc_unsupported_reason(x, N, int(D), T, K) == nullptr;
+        use_tc = tc_unsupported_reason(x, N, int(D), T, K, int(sizeof(XT))) == nullptr;
     } else {
         VQ_REQUIRE(algo == VQ_ALGO_SIMT, "unknown algo");
     }
@@ -213,25 +215,33 @@ static int assign_impl(const float* x, int64_t N, int64_t D, int64_t T, const fl
             return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d, scalars,
                                       (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr, hint_dev);
         };
-        if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1>));
-        else if (vec) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 4>));
-        else if (D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<false, 1>));
-        else VQ_CUDA_OK(launch_list(assign_list_kernel<false, 4>));
+        if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1, XT>));
+        else if (vec) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 4, XT>));
+        else if (D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<false, 1, XT>));
+        else VQ_CUDA_OK(launch_list(assign_list_kernel<false, 4, XT>));
     } else {
         int64_t tiles = N * ((T + S_BM - 1) / S_BM);
         int grid = int(std::min<int64_t>(tiles, int64_t(num_sms()) * 16));
-        assign_simt_kernel<<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars);
+        assign_simt_kernel<XT><<<grid, 256, 0, stream>>>(x, N, int(D), T, k, w.ee, K, idx, min_d, scalars);
         VQ_CUDA_OK(cudaGetLastError());
         prof_mark(pslot, 2, stream);
     }
     prof_mark(pslot, 3, stream);
     return 0;
 }
+}  // extern "C++"
 
 int vq_assign(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,
               int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
               int algo, void* stream) {
     return assign_impl(x, N, D, T, k, K, idx, min_d, scalars, workspace, workspace_bytes, algo, stream, nullptr);
+}
+
+int vq_assign_bf16(const void* x_bf16, int64_t N, int64_t D, int64_t T, const float* k, int K,
+                   int64_t* idx, float* min_d, double* scalars, void* workspace, size_t workspace_bytes,
+                   int algo, void* stream) {
+    return assign_impl(static_cast<const __nv_bfloat16*>(x_bf16), N, D, T, k, K, idx, min_d, scalars, workspace, workspace_bytes, algo, stream,
+                       nullptr);
 }
 
 int vq_assign_debug(const float* x, int64_t N, int64_t D, int64_t T, const float* k, int K,

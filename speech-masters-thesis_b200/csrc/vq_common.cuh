@@ -77,6 +77,10 @@ inline cudaError_t ensure_dynamic_smem(F* func, int bytes) {
     return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(func), bytes);
 }
 
+// latents come as FP32 or (bf16 autocast training / inference) as BF16; every kernel that reads them is templated on the type
+__device__ __forceinline__ float x_to_float(float v) { return v; }
+__device__ __forceinline__ float x_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

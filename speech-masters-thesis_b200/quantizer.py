@@ -94,9 +94,13 @@ def invalidate_prepared():
 
 # --------------------------------------------------------------------------------------- raw ops
 def assign(x, k, algo="auto", want_min_d=False, scalars=None):
-    """K1 on an NCT tensor: returns (idx [N,T] int64, min_d [N,T] fp32 or None)."""
+    """K1 on an NCT tensor (fp32, or bf16 as a bf16-autocast encoder emits it -- no up-cast pass): returns
+    (idx [N,T] int64, min_d [N,T] fp32 or None)."""
     lib = _lib.load()
     _require_cuda(x, "x")
+    entry = lib.vq_assign_bf16 if x.dtype == torch.bfloat16 else lib.vq_assign
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
     n, d, t = x.shape
     kk = k.shape[0]
     idx = torch.empty((n, t), dtype=torch.int64, device=x.device)
@@ -106,8 +110,8 @@ def assign(x, k, algo="auto", want_min_d=False, scalars=None):
     ws = _Workspace.get(x.device, n, t, kk, d)
     flag = _Workspace.prepared_flag(x.device, ws, k)
     with torch.cuda.device(x.device):
-        check(lib.vq_assign(ptr(x), n, d, t, ptr(k), kk, ptr(idx), ptr(min_d), ptr(scalars), ptr(ws), ws.numel(),
-                            _lib.ALGOS[algo] | flag, _stream(x)), "vq_assign")
+        check(entry(ptr(x), n, d, t, ptr(k), kk, ptr(idx), ptr(min_d), ptr(scalars), ptr(ws), ws.numel(),
+                    _lib.ALGOS[algo] | flag, _stream(x)), "vq_assign")
     return idx, min_d
 
 
@@ -176,7 +180,7 @@ class _QuantizeST(torch.autograd.Function):
     """Forward: K1 + K2.  Backward: straight-through + commitment gradient (only ``x`` gets a gradient)."""
 
     @staticmethod
-    def forward(ctx, x, mask, k, algo, after_assign, fused_stats, group=None):
+    def forward(ctx, x, mask, k, algo, after_assign, fused_stats, group=None, x_assign=None):
         lib = _lib.load()
         n, d, t = x.shape
         kk = k.shape[0]
@@ -186,7 +190,9 @@ class _QuantizeST(torch.autograd.Function):
         if group is not None:                  # (tok, n_vocab, l_bins): phoneme-conditioned codebook subsets
             rel, idx = assign_grouped(x, k, *group)
         else:
-            idx, _ = assign(x, k, algo)        # indices only; K2 accumulates the `fit` numerator
+            # indices only; K2 accumulates the `fit` numerator.  (x_assign: the bf16 original of x when the caller up-cast it
+            # for K2 / K3 -- K1 reads the bf16 tensor directly)
+            idx, _ = assign(x if x_assign is None else x_assign, k, algo)
         if after_assign is not None:
             # EMA statistics (K3a) and their all-reduce are issued here, BEFORE K2: the collective then overlaps K2,
             # which does not depend on it (K1 -> K3a -> {all-reduce || K2} -> K3b)
@@ -223,7 +229,7 @@ class _QuantizeST(torch.autograd.Function):
             with torch.cuda.device(x.device):
                 check(lib.vq_gather_st_bwd(ptr(x), ptr(idx), ptr(mask), ptr(k), ptr(g_xq), ptr(g_commit), ptr(scalars),
                                            n, d, t, k.shape[0], ptr(grad_x), _stream(x)), "vq_gather_st_bwd")
-        return grad_x, None, None, None, None, None, None
+        return grad_x, None, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- modules
@@ -426,13 +432,13 @@ class BottleneckBlock(nn.Module):
         return out[0].t().contiguous().view(*x_l.shape, self.emb_width)
 
     # ---- NCT entry points
-    def _check_input(self, x, mask):
+    def _check_input(self, x, mask, keep_bf16=False):
         _require_cuda(x, "x")
         if x.shape[1] == 2 * self.emb_width:                              # bottleneck.py:105-113 (unused by the configs)
             x = x[:, :self.emb_width] + x[:, self.emb_width:]
         assert x.shape[1] == self.emb_width, f"Expected {x.shape[1]} to be (1 or 2) * {self.emb_width}"
         x = x.contiguous()
-        if x.dtype != torch.float32:
+        if x.dtype != torch.float32 and not (keep_bf16 and x.dtype == torch.bfloat16):
             x = x.float()
         if mask is not None:
             mask = mask.to(torch.float32).contiguous()
@@ -441,7 +447,7 @@ class BottleneckBlock(nn.Module):
 
     def encode(self, x, mask):
         """bottleneck.py:147-158: [N, D, T] -> [N, T] int64 (K1 only; padded frames get an index too)."""
-        x, mask = self._check_input(x.detach(), mask)
+        x, mask = self._check_input(x.detach(), mask, keep_bf16=True)     # bf16 latents go to K1 as they are
         idx, _ = assign(x, self.k, self.algo)
         return idx
 
@@ -452,7 +458,8 @@ class BottleneckBlock(nn.Module):
 
     def forward(self, x, mask, update_k=True):
         """bottleneck.py:171-201 -> (x_l [N,T] int64, x_q [N,D,T], commit_loss, metrics)."""
-        x, mask = self._check_input(x, mask)
+        x_bf16 = x.detach().contiguous() if (x.dtype == torch.bfloat16 and x.shape[1] == self.emb_width) else None
+        x, mask = self._check_input(x, mask)          # (K2 / K3 read FP32: bf16 latents are up-cast for them; K1 reads the original)
         if update_k and not self.init:
             with torch.no_grad():
                 self._set_codebook(self._restart_rows_nct(x.detach(), mask))      # init_k (:179-180)
@@ -462,7 +469,7 @@ class BottleneckBlock(nn.Module):
             fused_stats = torch.zeros(dist.stats_numel(self.k_bins, self.emb_width), dtype=torch.float32, device=x.device)
         elif update_k:
             hook = lambda x_l: pending.append(self._ema_begin(x.detach(), x_l, mask))
-        x_l, x_q, commit_loss, scalars, results, _ = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook, fused_stats)
+        x_l, x_q, commit_loss, scalars, results, _ = _QuantizeST.apply(x, mask, k.contiguous(), self.algo, hook, fused_stats, None, x_bf16)
         if update_k:
             if fused_stats is not None:
                 pending.append(self._ema_begin(x.detach(), x_l, mask, stats=fused_stats))

@@ -108,6 +108,32 @@ def test_tcgen05_route_for_t_not_a_multiple_of_4(vq, shape, clustered):
         audit(xp, code, idx2)
 
 
+@pytest.mark.parametrize("shape", [(8, 128, 1024, 512, True), (8, 128, 1024, 512, False), (3, 64, 136, 1024, False), (2, 256, 72, 8192, True),
+                                   (2, 128, 37, 512, False)],
+                         ids=lambda s: f"N{s[0]}_D{s[1]}_T{s[2]}_K{s[3]}_{'c' if s[4] else 'g'}")
+def test_bf16_latents_without_upcast(vq, shape):
+    """vq_assign_bf16: bf16 latents straight into K1 (tcgen05 route when T % 8 == 0, the exact CUDA-core kernel otherwise) must
+    give the indices of the oracle run on x.float() -- the reference semantics for a bf16-autocast encoder."""
+    n, D, t, K, clustered = shape
+    gen = torch.Generator().manual_seed(t + K)
+    code = torch.randn(K, D, generator=gen)
+    lengths = torch.full((n,), t)
+    x, mask = O.synthetic_batch(lengths, D, gen, codebook=code if clustered else None)
+    xb = x.to(torch.bfloat16)
+    for algo in ("auto", "simt"):
+        idx, min_d = vq.assign(xb.to(DEV), code.to(DEV), algo=algo, want_min_d=True)
+        rep = audit(xb.float(), code, idx)
+        rows = xb.float().permute(0, 2, 1).reshape(-1, D)
+        o_l, o_min = O.assign_chunked(rows, code)
+        if rep["mismatches"] == 0:
+            assert torch.allclose(min_d.cpu().reshape(-1), o_min, rtol=2e-5, atol=2e-4)
+    # the module's encode takes bf16 as it is
+    blk = vq.BottleneckBlock(K, D, 0.99, 1.0).to(DEV)
+    blk.k, blk.init = code.to(DEV), True
+    z = blk.encode(xb.to(DEV), mask.to(DEV))
+    audit(xb.float(), code, z)
+
+
 def test_second_device_gets_its_shared_memory_opt_in(vq):
     """cudaFuncSetAttribute is per device: the same process must be able to run the kernels on cuda:1 after cuda:0."""
     if torch.cuda.device_count() < 2:
