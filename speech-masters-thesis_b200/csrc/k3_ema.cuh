@@ -49,7 +49,7 @@ template <> struct ErCfg<true>  { static constexpr int DW = 64,  STAGES = 5; }; 
 template <> struct ErCfg<false> { static constexpr int DW = 128, STAGES = 6; };
 template <bool SLAB> constexpr int er_stage_bytes() { return ErCfg<SLAB>::DW * ER_XS * 4 + ER_TT * 8 + ER_TT * 4; }
 template <bool SLAB> inline size_t er_smem_bytes(int K) {
-    return size_t(ErCfg<SLAB>::STAGES) * er_stage_bytes<SLAB>() + 2 * ER_TT * 4 + (SLAB ? (size_t(K) * ErCfg<true>::DW + K) * 4 : 0);
+    return size_t(ErCfg<SLAB>::STAGES) * er_stage_bytes<SLAB>() + 3 * ER_TT * 4 + (SLAB ? (size_t(K) * ErCfg<true>::DW + K) * 4 : 0);
 }
 
 template <bool SLAB>
@@ -60,8 +60,8 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
     constexpr int DW = ErCfg<SLAB>::DW, STAGES = ErCfg<SLAB>::STAGES, NQ = DW / 32, STAGE_BYTES = er_stage_bytes<SLAB>();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* stage0 = smem_raw;
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw + size_t(STAGES) * STAGE_BYTES);   // [2][ER_TT] keys, ~0u = no row
-    float* slab = reinterpret_cast<float*>(sorted + 2 * ER_TT);                               // [K][DW]   (SLAB only)
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(smem_raw + size_t(STAGES) * STAGE_BYTES);   // [2][ER_TT] sorted keys (>= 0xFFFFFF00: no row) + [ER_TT] scratch
+    float* slab = reinterpret_cast<float*>(sorted + 3 * ER_TT);                               // [K][DW]   (SLAB only)
     float* scnt = slab + size_t(K) * DW;                                                       // [K]       (SLAB, slice 0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d0 = SLAB ? blockIdx.y * DW : 0;
@@ -160,44 +160,39 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
         cp_async_commit();
     };
 
-    // keys of a tile: (code << 8) | frame for valid rows, ~0u otherwise; 64 keys = 2 per lane, bitonic sort in one warp
+    // keys of a tile: (code << 8) | frame for valid rows, 0xFFFFFF00 | frame otherwise (all distinct); 64 keys = 2 per lane.
+    // Sorted by RANK: every lane counts how many of the 64 keys are smaller than each of its two (16 broadcast 16-byte loads, 128
+    // independent compare-adds) and stores its keys at those positions.  A bitonic network needs 21 dependent shuffle stages
+    // (~1300 cycles of latency on this one warp, the longest chain of an iteration); the rank count has no chain at all.
     auto sort_tile = [&](bool exists, int st, uint32_t* out) {
         if (!exists) return;
         const float* Xs = reinterpret_cast<const float*>(stage0 + size_t(st) * STAGE_BYTES);
         const int64_t* s_idx = reinterpret_cast<const int64_t*>(Xs + DW * ER_XS);
         const float* s_mask = reinterpret_cast<const float*>(s_idx + ER_TT);
+        uint32_t* tmp = sorted + 2 * ER_TT;
         uint32_t key[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int t = r * 32 + lane;
             const int64_t ci = s_idx[t];
-            key[r] = (s_mask[t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : 0xFFFFFFFFu;
+            key[r] = (s_mask[t] != 0.f && ci >= 0) ? ((uint32_t(min(ci, int64_t(K - 1))) << 8) | uint32_t(t)) : (0xFFFFFF00u | uint32_t(t));
+            tmp[t] = key[r];
         }
-#if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 2048)     /* timing experiment: no sorting network (wrong results) */
-        for (int k = 2; k <= 0; k <<= 1) {
+        __syncwarp();
+#if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 2048)     /* timing experiment: no sorting (wrong results) */
+        int rank0 = lane, rank1 = 32 + lane;
 #else
+        int rank0 = 0, rank1 = 0;
 #pragma unroll
-        for (int k = 2; k <= ER_TT; k <<= 1) {
-#endif
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j >= 32) {                     // j == 32, k == 64: partner is the lane's other key, ascending
-                    const uint32_t a = key[0], b = key[1];
-                    key[0] = min(a, b);
-                    key[1] = max(a, b);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
-                        const int i = r * 32 + lane;
-                        const bool up = (i & k) == 0, lower = (lane & j) == 0;
-                        key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
-                    }
-                }
-            }
+        for (int j4 = 0; j4 < ER_TT / 4; ++j4) {
+            const uint4 q = reinterpret_cast<const uint4*>(tmp)[j4];
+            rank0 += int(q.x < key[0]) + int(q.y < key[0]) + int(q.z < key[0]) + int(q.w < key[0]);
+            rank1 += int(q.x < key[1]) + int(q.y < key[1]) + int(q.z < key[1]) + int(q.w < key[1]);
         }
-        out[lane] = key[0];
-        out[32 + lane] = key[1];
+#endif
+        out[rank0] = key[0];
+        out[rank1] = key[1];
+        __syncwarp();                                  // (tmp is rewritten by this warp's next call)
     };
 
     for (;;) {
@@ -227,10 +222,10 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
                 int i = lo;
                 const uint32_t kprev = (lo > 0 && lo < ER_TT) ? keys[lo - 1] : 0xFFFFFFFFu;
                 // skip the tail of a run that started in an earlier warp's range
-                while (i < hi && keys[i] != 0xFFFFFFFFu && (keys[i] >> 8) == (kprev >> 8)) ++i;
+                while (i < hi && keys[i] < 0xFFFFFF00u && (keys[i] >> 8) == (kprev >> 8)) ++i;
                 while (i < hi) {
                     uint32_t key = keys[i];
-                    if (key == 0xFFFFFFFFu) break;                                // sorted: no more rows
+                    if (key >= 0xFFFFFF00u) break;                                // sorted: no more rows
                     const uint32_t code = key >> 8;
                     float a[NQ];
 #pragma unroll
@@ -244,7 +239,7 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
                         cnt += 1.f;
                         ++i;
                         key = i < ER_TT ? keys[i] : 0xFFFFFFFFu;
-                    } while (key != 0xFFFFFFFFu && (key >> 8) == code);
+                    } while (key < 0xFFFFFF00u && (key >> 8) == code);
 #if defined(VQ_EXPERIMENT) && (VQ_EXPERIMENT & 256)      /* timing experiment: no updates */
                     if (a[0] + cnt == -12345.f) sums[0] = 1.f;
 #else
