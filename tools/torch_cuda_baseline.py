@@ -63,6 +63,24 @@ def main():
         out[f"utt{n_utt}"] = res
         del xd, md, r, mcol, valid, idx
         torch.cuda.empty_cache()
+    # the UNMODIFIED reference module itself (staged copy, baseline/_ref) with stock PyTorch CUDA ops, BASELINE.json configs[0] shape
+    from oracle import stage_ref
+    if stage_ref.activate():
+        from models.vqvae.bottleneck import BottleneckBlock
+        lengths = O.ljspeech_like_lengths(16, gen)
+        x, mask = O.synthetic_batch(lengths, D, gen, codebook=code)
+        xd, md = x.to(dev), mask.to(dev)
+        blk = BottleneckBlock(K, D, 0.99, 1.0).to(dev)
+        blk.k = code.clone().to(dev)
+        blk.k_sum, blk.k_elem, blk.init = (code * 4).to(dev), torch.full((K,), 4.0, device=dev), True
+        blk.train()
+        with torch.no_grad():
+            fwd = timeit(lambda: blk(xd, md, update_k=True), reps=5)
+            enc = timeit(lambda: blk.encode(xd, md), reps=5)
+        valid = int(lengths.sum())
+        out["reference_module_cuda_b16"] = {"rows": x.shape[0] * x.shape[2], "valid_frames": valid, "forward_train_ms": fwd, "encode_ms": enc,
+                                            "forward_train_valid_frames_per_s": valid / (fwd * 1e-3), "encode_valid_frames_per_s": valid / (enc * 1e-3),
+                                            "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/torch_cuda_baseline.json", "w"), indent=1)
     print(json.dumps(out))
