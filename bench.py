@@ -405,6 +405,9 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
+    if world > 1:
+        dist.destroy_process_group()      # no collective after this point: the CPU baseline below runs the reference module
+        # (it would otherwise try to broadcast CPU tensors over NCCL, bottleneck.py:72-75)
     ms, e2e_ms, fwd_ms, fwd_fast_ms, fwd_graph_ms, sus_ms, g_ms, c5_ms, grouped_ms = (float(times[i]) for i in range(9))
     tot_codes5 = float(frames[4])
     tot_valid, tot_rows, g_tot_valid = float(frames[0]), float(frames[1]), float(frames[2])
@@ -564,8 +567,6 @@ def run_b200(args):
         "unsafe_rows_per_step": unsafe,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
