@@ -181,6 +181,26 @@ int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old,
                     int k_bins, int emb_width, double mu, double threshold, double laplace_eps,
                     double* scalars, float* results, int64_t* used_curr, void* stream);
 
+/* ---- the one exchange step of the path over NVLink peer memory (one process per GPU, one node) ------------------------
+ * Replaces distributed.broadcast(_k_rand, 0) + all_reduce(_k_sum) + all_reduce(_k_elem) (bottleneck.py:72-75).  Every rank
+ * allocates a REGION with vq_p2p_alloc, sends the 64-byte handle to its peers (any transport: the Python module uses
+ * torch.distributed.all_gather_object once, at set-up) and maps theirs with vq_p2p_open.  Per training step `step` (1, 2, ...,
+ * the same on all ranks) a rank lets vq_ema_accumulate add into vq_p2p_stats_slot(own region, step) (zeroed first) and
+ * writes its restart rows to vq_p2p_krand_slot(own region, step); vq_p2p_exchange then publishes a flag in every peer's
+ * region, waits for all peers' flags, and writes the sum over ranks of the statistics (summed in rank order: bit-identical
+ * on every rank) to stats_out [K*D + K] and rank 0's restart rows to k_rand_out [K*D] -- the inputs of vq_ema_finalize.
+ * `regions` is a HOST array of n_ranks device pointers (this rank's own region at index `rank`, the peers' mappings
+ * elsewhere), n_ranks <= 16.  Everything is enqueued on `stream`; a peer that never arrives traps after seconds. */
+size_t vq_p2p_region_bytes(int k_bins, int emb_width);
+int    vq_p2p_alloc(size_t bytes, void** region_out, unsigned char* handle64_out);
+int    vq_p2p_open(const unsigned char* handle64, void** region_out);
+int    vq_p2p_close(void* peer_region);
+int    vq_p2p_free(void* region);
+float* vq_p2p_stats_slot(void* region, unsigned int step, int k_bins, int emb_width);
+float* vq_p2p_krand_slot(void* region, unsigned int step, int k_bins, int emb_width);
+int    vq_p2p_exchange(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
+                       float* stats_out, float* k_rand_out, void* stream);
+
 /* Gather K rows of the flattened [N*T, D] view of an NCT tensor: out[j,:] = x[n_j, :, t_j] with
  * row = n*T + t.  Used for the restart rows y[randperm][:K] (bottleneck.py:40,70) so that only K rows
  * are touched instead of a full permuted copy. */

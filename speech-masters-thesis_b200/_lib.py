@@ -48,6 +48,14 @@ SIGNATURES = {
     "vq_ema_accumulate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "vq_ema_finalize": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                  _c_double, _c_double, _c_double, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "vq_p2p_region_bytes": (_c_size_t, [_c_int, _c_int]),
+    "vq_p2p_alloc": (_c_int, [_c_size_t, _c_void_p, _c_void_p]),
+    "vq_p2p_open": (_c_int, [_c_void_p, _c_void_p]),
+    "vq_p2p_close": (_c_int, [_c_void_p]),
+    "vq_p2p_free": (_c_int, [_c_void_p]),
+    "vq_p2p_stats_slot": (_c_void_p, [_c_void_p, ctypes.c_uint, _c_int, _c_int]),
+    "vq_p2p_krand_slot": (_c_void_p, [_c_void_p, ctypes.c_uint, _c_int, _c_int]),
+    "vq_p2p_exchange": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_uint, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "vq_gather_rows": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_void_p, _c_void_p]),
     "vq_restart_rows_device": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_uint64, _c_void_p, _c_void_p,
                                         _c_void_p, _c_void_p]),

@@ -7,6 +7,7 @@
 #include "k2_gather.cuh"
 #include "k2_fused_ema.cuh"
 #include "k3_ema.cuh"
+#include "k3_p2p.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -399,6 +400,69 @@ int vq_ema_finalize(const float* stats, const float* k_rand, const float* k_old,
     ema_finalize_kernel<<<grid, 256, 0, stream>>>(stats, k_rand, k_old, k, k_sum, k_elem, K, D, float(mu), float(1.0 - mu),
                                                   float(threshold), float(laplace_eps), scalars, results, used_curr,
                                                   (unsigned int)grid);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- EMA statistics exchange over NVLink peer memory (k3_p2p.cuh)
+size_t vq_p2p_region_bytes(int k_bins, int emb_width) {
+    return (k_bins > 0 && emb_width > 0) ? p2p_region_bytes(k_bins, emb_width) : 0;
+}
+
+int vq_p2p_alloc(size_t bytes, void** region_out, unsigned char* handle64_out) {
+    VQ_REQUIRE(region_out && handle64_out && bytes >= P2P_FLAG_BYTES, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* ptr = nullptr;
+    VQ_CUDA_OK(cudaMalloc(&ptr, bytes));
+    VQ_CUDA_OK(cudaMemset(ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    memcpy(handle64_out, &h, 64);
+    *region_out = ptr;
+    return 0;
+}
+
+int vq_p2p_open(const unsigned char* handle64, void** region_out) {
+    VQ_REQUIRE(handle64 && region_out, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    VQ_CUDA_OK(cudaIpcOpenMemHandle(region_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int vq_p2p_close(void* peer_region) {
+    if (peer_region) VQ_CUDA_OK(cudaIpcCloseMemHandle(peer_region));
+    return 0;
+}
+
+int vq_p2p_free(void* region) {
+    if (region) VQ_CUDA_OK(cudaFree(region));
+    return 0;
+}
+
+float* vq_p2p_stats_slot(void* region, unsigned int step, int k_bins, int emb_width) {
+    return region ? p2p_stats_slot(region, step, p2p_stats_floats(k_bins, emb_width)) : nullptr;
+}
+
+float* vq_p2p_krand_slot(void* region, unsigned int step, int k_bins, int emb_width) {
+    return region ? p2p_krand_slot(region, step, p2p_stats_floats(k_bins, emb_width), size_t(k_bins) * emb_width) : nullptr;
+}
+
+int vq_p2p_exchange(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
+                    float* stats_out, float* k_rand_out, void* stream_) {
+    VQ_REQUIRE(regions && stats_out && k_rand_out, "null pointer");
+    VQ_REQUIRE(n_ranks >= 1 && n_ranks <= P2P_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank / world size (at most 16 ranks)");
+    VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    P2PPeers peers;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) peers.region[r] = r < n_ranks ? regions[r] : nullptr;
+    for (int r = 0; r < n_ranks; ++r) VQ_REQUIRE(peers.region[r] != nullptr, "a peer region is not mapped");
+    const size_t sf = p2p_stats_floats(k_bins, emb_width), kf = size_t(k_bins) * emb_width;
+    p2p_publish_kernel<<<1, 32, 0, stream>>>(peers, n_ranks, rank, step);
+    p2p_wait_kernel<<<1, 32, 0, stream>>>(static_cast<const unsigned*>(regions[rank]), n_ranks, step);
+    const int grid = int(std::min<size_t>((sf + 255) / 256, size_t(num_sms()) * 4));
+    p2p_reduce_kernel<<<grid, 256, 0, stream>>>(peers, n_ranks, step, sf, kf, stats_out, k_rand_out);
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

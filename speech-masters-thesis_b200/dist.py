@@ -5,6 +5,10 @@ statistics ``[K*D sums | K counts]`` (reference: two all_reduce calls, bottlenec
 restart rows riding along as a zero-padded slab (reference: a broadcast, bottleneck.py:73) -- a SUM over
 ``{rows, 0, 0, ...}`` is a broadcast.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests).
 """
+import ctypes
+import os
+import socket
+
 import torch
 import torch.distributed as distributed
 
@@ -49,6 +53,87 @@ def allreduce_statistics(stats, k_rand, k_bins, emb_width, async_op=False):
     distributed.broadcast(k_rand, 0)
     work = distributed.all_reduce(stats, distributed.ReduceOp.SUM, async_op=async_op)
     return (k_rand, work) if async_op else k_rand
+
+
+class _DeviceView:
+    """Zero-copy view of raw device memory for ``torch.as_tensor`` (CUDA array interface)."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """The EMA statistics exchange over NVLink peer memory (csrc/k3_p2p.cuh) instead of NCCL: every rank exports one region with
+    CUDA IPC, maps its peers' regions once, and from then on a step costs three tiny kernels (publish a flag in every peer,
+    wait for all flags, sum the peers' statistics in rank order).  ``create`` is a collective (handle exchange through the
+    default process group) and returns None on every rank when any rank cannot take part (other backend, several nodes,
+    IPC / peer access unavailable, ``VQ_P2P=0``): the module then keeps the NCCL all-reduce."""
+
+    def __init__(self):
+        self.regions = None
+
+    def __deepcopy__(self, memo):          # mappings are per process and per module: a copied module sets up its own on first use
+        return None
+
+    @classmethod
+    def create(cls, k_bins, emb_width, device):
+        from . import _lib
+        n_ranks, rank = world()
+        if n_ranks == 1 or device.type != "cuda":
+            return None
+        lib = _lib.load()
+        self = cls()
+        self.lib, self.k_bins, self.emb_width, self.device = lib, k_bins, emb_width, device
+        self.n_ranks, self.rank, self.step = n_ranks, rank, 0
+        ok = os.environ.get("VQ_P2P", "1") != "0" and distributed.get_backend() == "nccl" and n_ranks <= 16
+        region, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        if ok:
+            with torch.cuda.device(device):
+                ok = lib.vq_p2p_alloc(int(lib.vq_p2p_region_bytes(k_bins, emb_width)), ctypes.byref(region), handle) == 0
+        infos = [None] * n_ranks
+        distributed.all_gather_object(infos, (bool(ok), socket.gethostname(), bytes(handle)))
+        ok = all(i[0] for i in infos) and len({i[1] for i in infos}) == 1
+        regions = (ctypes.c_void_p * n_ranks)()
+        if ok:
+            with torch.cuda.device(device):
+                for r, (_, _, h) in enumerate(infos):
+                    if r == rank:
+                        regions[r] = region.value
+                    else:
+                        peer = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                        if lib.vq_p2p_open(buf, ctypes.byref(peer)) != 0:
+                            ok = False
+                            break
+                        regions[r] = peer.value
+        flags = [None] * n_ranks
+        distributed.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            return None
+        self.regions, self.own = regions, region.value
+        return self
+
+    def _view(self, ptr, numel):
+        return torch.as_tensor(_DeviceView(ptr, numel), device=self.device)
+
+    def begin_step(self):
+        """Next step: (statistics slot [K*D + K], restart-row slot [K, D]) of this rank's region, for K3a / the restart rows."""
+        self.step += 1
+        kd = self.k_bins * self.emb_width
+        stats = self._view(self.lib.vq_p2p_stats_slot(self.own, self.step, self.k_bins, self.emb_width), kd + self.k_bins)
+        k_rand = self._view(self.lib.vq_p2p_krand_slot(self.own, self.step, self.k_bins, self.emb_width), kd).view(self.k_bins, self.emb_width)
+        return stats, k_rand
+
+    def exchange(self, stream):
+        """Publish this rank's slots of the current step, wait for all peers, return (summed statistics, rank 0's restart rows)."""
+        from ._lib import check
+        kd = self.k_bins * self.emb_width
+        stats = torch.empty(kd + self.k_bins, dtype=torch.float32, device=self.device)
+        k_rand = torch.empty((self.k_bins, self.emb_width), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.vq_p2p_exchange(self.regions, self.n_ranks, self.rank, self.step, self.k_bins, self.emb_width,
+                                           stats.data_ptr(), k_rand.data_ptr(), stream), "vq_p2p_exchange")
+        return stats, k_rand
 
 
 def shard_range(n_items, n_ranks, rank):

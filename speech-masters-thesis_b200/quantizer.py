@@ -332,24 +332,41 @@ class BottleneckBlock(nn.Module):
         n, d, t = x.shape
         return bool(_lib.load().vq_gather_st_fwd_ema_supported(d, t, self.k_bins))
 
+    def _peer_exchange(self, device):
+        """The NVLink peer-memory exchange (dist.PeerExchange), created on the first multi-rank training step (a collective)."""
+        if getattr(self, "_peer", None) is None:
+            self._peer = dist.PeerExchange.create(self.k_bins, self.emb_width, device) or False
+        return self._peer or None
+
     def _ema_begin(self, x, x_l, mask, k_rand=None, stats=None):
-        """K3a on the current stream, then the ONE collective of the path, asynchronously.  Returns the pending state for
-        ``_ema_finish``.  With ``rng_parity`` the restart rows need a host round trip (``nonzero`` + CPU ``randperm``);
-        that is deferred to ``_ema_finish`` so K1 / K3a / K2 are all in flight before the host blocks."""
+        """K3a on the current stream, then the ONE exchange of the path.  Returns the pending state for ``_ema_finish``.
+        Multi-rank: statistics go straight into this rank's peer-visible slot (dist.PeerExchange) and are summed over NVLink
+        in ``_ema_finish``; where that is unavailable, ONE NCCL all-reduce is issued here, asynchronously, so that it overlaps K2.
+        With ``rng_parity`` the restart rows need a host round trip (``nonzero`` + CPU ``randperm``); that is deferred to
+        ``_ema_finish`` so K1 / K3a / K2 are all in flight before the host blocks."""
         lib = _lib.load()
         n, d, t = x.shape
         kk = self.k_bins
         with torch.no_grad():
+            peer = self._peer_exchange(x.device) if dist.world()[0] > 1 else None
+            k_slot = None
             if stats is None:                    # (else: the fused K2 + K3a kernel already accumulated into `stats`)
-                stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
+                if peer is not None:
+                    stats, k_slot = peer.begin_step()
+                    stats.zero_()
+                else:
+                    stats = torch.zeros(dist.stats_numel(kk, d), dtype=torch.float32, device=x.device)
                 with torch.cuda.device(x.device):
                     scratch = torch.empty(n * ((t + 63) // 64), dtype=torch.uint8, device=x.device) if mask is not None else None
                     check(lib.vq_ema_accumulate(ptr(x), ptr(x_l), ptr(mask), n, d, t, kk, ptr(stats), ptr(scratch), _stream(x)),
                           "vq_ema_accumulate")
-            pending = dict(stats=stats, k_rand=k_rand, work=None, x=x, mask=mask)
+            elif peer is not None:
+                own, k_slot = peer.begin_step()
+                own.copy_(stats[:own.numel()])
+            pending = dict(stats=stats, k_rand=k_rand, work=None, x=x, mask=mask, peer=peer, k_slot=k_slot)
             if k_rand is None and not self.rng_parity:
                 pending["k_rand"] = self._restart_rows_nct(x, mask)        # device-side draw: no host sync
-            if pending["k_rand"] is not None:
+            if pending["k_rand"] is not None and peer is None:
                 # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
                 # here ONE all-reduce of the packed buffer (see dist.py), overlapped with K2
                 pending["k_rand"], pending["work"] = dist.allreduce_statistics(stats, pending["k_rand"], kk, d, async_op=True)
@@ -357,13 +374,17 @@ class BottleneckBlock(nn.Module):
 
     def _ema_finish(self, pending, scalars, results):
         lib = _lib.load()
-        stats, k_rand, x = pending["stats"], pending["k_rand"], pending["x"]
+        stats, k_rand, x, peer = pending["stats"], pending["k_rand"], pending["x"], pending["peer"]
         kk, d = self.k_bins, self.emb_width
         with torch.no_grad():
             if k_rand is None:                                               # rng_parity: host RNG replay, after K2 was launched
                 k_rand = self._restart_rows_nct(x, pending["mask"])
-                k_rand, pending["work"] = dist.allreduce_statistics(stats, k_rand, kk, d, async_op=True)
-            if pending["work"] is not None:
+                if peer is None:
+                    k_rand, pending["work"] = dist.allreduce_statistics(stats, k_rand, kk, d, async_op=True)
+            if peer is not None:
+                pending["k_slot"].copy_(k_rand)                              # (only rank 0's rows are read by the peers)
+                stats, k_rand = peer.exchange(_stream(x))                    # publish, wait for the peers, sum in rank order
+            elif pending["work"] is not None:
                 pending["work"].wait()                                       # the current stream waits for the collective
             k_new = torch.empty_like(self.k)
             used_curr = torch.empty((), dtype=torch.int64, device=x.device)

@@ -252,9 +252,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, out, rng_parity):
+def _nccl_worker(rank, world, port, out, rng_parity, p2p):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["VQ_P2P"] = "1" if p2p else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world)
     try:
@@ -272,7 +273,8 @@ def _nccl_worker(rank, world, port, out, rng_parity):
             x_l, x_q, commit, metrics = blk(x[a:b].to(dev), mask[a:b].to(dev), update_k=True)
             res.append(dict(x_l=x_l.cpu(), commit=commit.cpu(), metrics={k: v.cpu() for k, v in metrics.items()}))
         torch.cuda.synchronize()
-        torch.save(dict(steps=res, k=blk.k.cpu(), k_sum=blk.k_sum.cpu(), k_elem=blk.k_elem.cpu()), f"{out}.{rank}")
+        torch.save(dict(steps=res, k=blk.k.cpu(), k_sum=blk.k_sum.cpu(), k_elem=blk.k_elem.cpu(), used_p2p=bool(getattr(blk, "_peer", None))),
+                   f"{out}.{rank}")
     finally:
         dist.destroy_process_group()
 
@@ -286,20 +288,23 @@ def _nccl_batch():
     return x, mask, code
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["nvlink_peer_memory", "nccl_allreduce"])
 @pytest.mark.parametrize("rng_parity", [True, False], ids=["rng_parity", "device_rng"])
-def test_two_rank_training_forward_over_nccl(vq, tmp_path, rng_parity):
-    """bottleneck.py:72-75 on hardware: 2 ranks, utterance-sharded batch, ONE NCCL all-reduce overlapped with K2.  Every
-    rank must end with bit-identical k / k_sum / k_elem, equal (1e-5) to the single-process oracle on the whole batch
-    (every code stays above the revival threshold, so the restart rows -- which come from rank 0's shard -- are unused)."""
+def test_two_rank_training_forward_over_nccl(vq, tmp_path, rng_parity, p2p):
+    """bottleneck.py:72-75 on hardware: 2 ranks, utterance-sharded batch; the statistics are exchanged over NVLink peer
+    memory (csrc/k3_p2p.cuh) or by ONE NCCL all-reduce overlapped with K2.  Every rank must end with bit-identical
+    k / k_sum / k_elem, equal (1e-5) to the single-process oracle on the whole batch (every code stays above the revival
+    threshold, so the restart rows -- which come from rank 0's shard -- are unused)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     out = str(tmp_path / "nccl")
-    mp.spawn(_nccl_worker, args=(2, _free_port(), out, rng_parity), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, rng_parity, p2p), nprocs=2, join=True)
     x, mask, code = _nccl_batch()
     K, D = code.shape
     st = O.CodebookState(K, D, 0.99, 1.0, code.clone(), code.clone() * 2, torch.full((K,), 2.0), True)
     got = [torch.load(f"{out}.{r}") for r in range(2)]
+    assert got[0]["used_p2p"] == got[1]["used_p2p"] and (got[0]["used_p2p"] or not p2p or os.environ.get("VQ_ALLOW_NO_P2P"))
     for name in ("k", "k_sum", "k_elem"):
         assert torch.equal(got[0][name], got[1][name]), name                    # replicas stay bit-identical
     rows, _, _ = O.flatten_nct(x, mask)
@@ -318,3 +323,41 @@ def test_two_rank_training_forward_over_nccl(vq, tmp_path, rng_parity):
     assert torch.allclose(got[0]["k_elem"], st.k_elem, rtol=1e-5, atol=1e-6)
     assert torch.allclose(got[0]["k_sum"], st.k_sum, rtol=1e-5, atol=1e-5)
     assert torch.allclose(got[0]["k"], st.k, rtol=1e-5, atol=1e-5)
+
+
+def _revival_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        import vqb200
+        dev = torch.device("cuda", rank)
+        x, mask, code = _nccl_batch()
+        a, b = vqb200.dist.shard_range(x.shape[0], world, rank)
+        K, D = code.shape
+        blk = vqb200.BottleneckBlock(K, D, 0.99, 1000.0).to(dev)          # threshold 1000: every code is re-seeded from k_rand
+        blk.k, blk.k_sum, blk.k_elem, blk.init = code.to(dev), code.to(dev).clone(), torch.ones(K, device=dev), True
+        blk.train()
+        torch.manual_seed(7 + rank)                                       # different RNG streams: only rank 0's rows may win
+        blk(x[a:b].to(dev), mask[a:b].to(dev), update_k=True)
+        torch.cuda.synchronize()
+        torch.save(dict(k=blk.k.cpu(), lo=a, hi=b), f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_revival_uses_rank0_rows(vq, tmp_path):
+    """bottleneck.py:73: the restart rows are rank 0's, on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "revive")
+    mp.spawn(_revival_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = [torch.load(f"{out}.{r}") for r in range(2)]
+    assert torch.equal(got[0]["k"], got[1]["k"])
+    x, mask, code = _nccl_batch()
+    rows0, _, valid0 = O.flatten_nct(x[got[0]["lo"]:got[0]["hi"]], mask[got[0]["lo"]:got[0]["hi"]])
+    pool = rows0[valid0]
+    dmin = (got[0]["k"][:64, None, :] - pool[None, :, :]).abs().amax(dim=2).min(dim=1).values
+    assert float(dmin.max()) == 0.0                                       # every new code is a valid frame of RANK 0's shard

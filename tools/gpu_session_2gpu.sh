@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi -L | head -4
-timeout 900 python -m pytest tests/test_gpu_audit.py -m gpu -q -k "nccl or second_device or two_streams" > gpurun_out/pytest_2gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_2gpu.log
+timeout 900 python -m pytest tests/test_gpu_audit.py -m gpu -q -k "nccl or second_device or two_streams or revival" > gpurun_out/pytest_2gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_2gpu.log
 tail -4 gpurun_out/pytest_2gpu.log
-python tools/ab_k1.py ab/libvqb200_r1.so speech-masters-thesis_b200/lib/libvqb200.so ab/libvqb200_ab1.so ab/libvqb200_ab16.so 2>&1 | tail -1 | tee gpurun_out/ab_bisect2.log
+
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err; echo "bench2 rc=$?"
 tail -c 400 gpurun_out/bench_2gpu.err
 python - <<'PY'
