@@ -111,6 +111,15 @@ class PeerExchange:
         if not all(flags):
             return None
         self.regions, self.own = regions, region.value
+        # the four slot views and the two pairs of output buffers are made once: a step must not pay for tensor construction
+        kd = k_bins * emb_width
+        self._slots, self._outs = [], []
+        for parity in (0, 1):
+            st = self._view(lib.vq_p2p_stats_slot(self.own, parity, k_bins, emb_width), kd + k_bins)
+            kr = self._view(lib.vq_p2p_krand_slot(self.own, parity, k_bins, emb_width), kd).view(k_bins, emb_width)
+            self._slots.append((st, kr))
+            self._outs.append((torch.empty(kd + k_bins, dtype=torch.float32, device=device),
+                               torch.empty((k_bins, emb_width), dtype=torch.float32, device=device)))
         return self
 
     def _view(self, ptr, numel):
@@ -119,17 +128,13 @@ class PeerExchange:
     def begin_step(self):
         """Next step: (statistics slot [K*D + K], restart-row slot [K, D]) of this rank's region, for K3a / the restart rows."""
         self.step += 1
-        kd = self.k_bins * self.emb_width
-        stats = self._view(self.lib.vq_p2p_stats_slot(self.own, self.step, self.k_bins, self.emb_width), kd + self.k_bins)
-        k_rand = self._view(self.lib.vq_p2p_krand_slot(self.own, self.step, self.k_bins, self.emb_width), kd).view(self.k_bins, self.emb_width)
-        return stats, k_rand
+        return self._slots[self.step & 1]
 
     def exchange(self, stream):
-        """Publish this rank's slots of the current step, wait for all peers, return (summed statistics, rank 0's restart rows)."""
+        """Publish this rank's slots of the current step, wait for all peers, return (summed statistics, rank 0's restart rows)
+        -- buffers owned by this object, valid until the exchange after next."""
         from ._lib import check
-        kd = self.k_bins * self.emb_width
-        stats = torch.empty(kd + self.k_bins, dtype=torch.float32, device=self.device)
-        k_rand = torch.empty((self.k_bins, self.emb_width), dtype=torch.float32, device=self.device)
+        stats, k_rand = self._outs[self.step & 1]
         with torch.cuda.device(self.device):
             check(self.lib.vq_p2p_exchange(self.regions, self.n_ranks, self.rank, self.step, self.k_bins, self.emb_width,
                                            stats.data_ptr(), k_rand.data_ptr(), stream), "vq_p2p_exchange")
