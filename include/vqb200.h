@@ -200,6 +200,11 @@ float* vq_p2p_stats_slot(void* region, unsigned int step, int k_bins, int emb_wi
 float* vq_p2p_krand_slot(void* region, unsigned int step, int k_bins, int emb_width);
 int    vq_p2p_exchange(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
                        float* stats_out, float* k_rand_out, void* stream);
+/* The two halves of vq_p2p_exchange, so that other work (K2) can be enqueued between them and hide the peers' latency:
+ * publish as soon as this rank's slots of `step` are written, collect (wait for all peers + rank-ordered sum) when needed. */
+int    vq_p2p_publish(void* const* regions, int n_ranks, int rank, unsigned int step, void* stream);
+int    vq_p2p_collect(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
+                      float* stats_out, float* k_rand_out, void* stream);
 
 /* Gather K rows of the flattened [N*T, D] view of an NCT tensor: out[j,:] = x[n_j, :, t_j] with
  * row = n*T + t.  Used for the restart rows y[randperm][:K] (bottleneck.py:40,70) so that only K rows

@@ -56,6 +56,8 @@ SIGNATURES = {
     "vq_p2p_stats_slot": (_c_void_p, [_c_void_p, ctypes.c_uint, _c_int, _c_int]),
     "vq_p2p_krand_slot": (_c_void_p, [_c_void_p, ctypes.c_uint, _c_int, _c_int]),
     "vq_p2p_exchange": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_uint, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "vq_p2p_publish": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_uint, _c_void_p]),
+    "vq_p2p_collect": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_uint, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "vq_gather_rows": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_void_p, _c_void_p]),
     "vq_restart_rows_device": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_uint64, _c_void_p, _c_void_p,
                                         _c_void_p, _c_void_p]),

@@ -55,9 +55,20 @@ __global__ void p2p_wait_kernel(const unsigned* my_flags, int n_ranks, unsigned 
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(P2PPeers peers, int n_ranks, unsigned step, size_t stats_floats, size_t krand_floats,
                                                         float* __restrict__ stats_out, float* __restrict__ k_rand_out) {
     const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = tid; i < stats_floats; i += nthreads) {
+    // 16-byte loads (the slots are 16-byte aligned when K*D + K is a multiple of 4; the tail goes element by element)
+    const bool vec = (stats_floats % 4 == 0) && (krand_floats % 4 == 0);
+    const size_t n4 = vec ? stats_floats / 4 : 0;
+    for (size_t i = tid; i < n4; i += nthreads) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < n_ranks; ++r) {                        // rank order: the same sum everywhere
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p2p_stats_slot(peers.region[r], step, stats_floats)) + i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        reinterpret_cast<float4*>(stats_out)[i] = s;
+    }
+    for (size_t i = n4 * 4 + tid; i < stats_floats; i += nthreads) {
         float s = 0.f;
-        for (int r = 0; r < n_ranks; ++r) s += __ldcg(p2p_stats_slot(peers.region[r], step, stats_floats) + i);    // rank order: the same sum everywhere
+        for (int r = 0; r < n_ranks; ++r) s += __ldcg(p2p_stats_slot(peers.region[r], step, stats_floats) + i);
         stats_out[i] = s;
     }
     const float* kr = p2p_krand_slot(peers.region[0], step, stats_floats, krand_floats);                              // rank 0's restart rows (bottleneck.py:73)

@@ -449,22 +449,41 @@ float* vq_p2p_krand_slot(void* region, unsigned int step, int k_bins, int emb_wi
     return region ? p2p_krand_slot(region, step, p2p_stats_floats(k_bins, emb_width), size_t(k_bins) * emb_width) : nullptr;
 }
 
-int vq_p2p_exchange(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
-                    float* stats_out, float* k_rand_out, void* stream_) {
-    VQ_REQUIRE(regions && stats_out && k_rand_out, "null pointer");
+static int p2p_peers(void* const* regions, int n_ranks, int rank, P2PPeers& peers) {
+    VQ_REQUIRE(regions, "null pointer");
     VQ_REQUIRE(n_ranks >= 1 && n_ranks <= P2P_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank / world size (at most 16 ranks)");
     VQ_REQUIRE(vq_device_supported(), "this library only runs on compute capability 10.x (B200); no fallback exists");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    P2PPeers peers;
     for (int r = 0; r < P2P_MAX_RANKS; ++r) peers.region[r] = r < n_ranks ? regions[r] : nullptr;
     for (int r = 0; r < n_ranks; ++r) VQ_REQUIRE(peers.region[r] != nullptr, "a peer region is not mapped");
-    const size_t sf = p2p_stats_floats(k_bins, emb_width), kf = size_t(k_bins) * emb_width;
-    p2p_publish_kernel<<<1, 32, 0, stream>>>(peers, n_ranks, rank, step);
-    p2p_wait_kernel<<<1, 32, 0, stream>>>(static_cast<const unsigned*>(regions[rank]), n_ranks, step);
-    const int grid = int(std::min<size_t>((sf + 255) / 256, size_t(num_sms()) * 4));
-    p2p_reduce_kernel<<<grid, 256, 0, stream>>>(peers, n_ranks, step, sf, kf, stats_out, k_rand_out);
+    return 0;
+}
+
+int vq_p2p_publish(void* const* regions, int n_ranks, int rank, unsigned int step, void* stream) {
+    P2PPeers peers;
+    if (p2p_peers(regions, n_ranks, rank, peers)) return 1;
+    p2p_publish_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(peers, n_ranks, rank, step);
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int vq_p2p_collect(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
+                   float* stats_out, float* k_rand_out, void* stream_) {
+    VQ_REQUIRE(stats_out && k_rand_out, "null pointer");
+    P2PPeers peers;
+    if (p2p_peers(regions, n_ranks, rank, peers)) return 1;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t sf = p2p_stats_floats(k_bins, emb_width), kf = size_t(k_bins) * emb_width;
+    p2p_wait_kernel<<<1, 32, 0, stream>>>(static_cast<const unsigned*>(regions[rank]), n_ranks, step);
+    const int grid = int(std::min<size_t>((sf / 4 + 255) / 256, size_t(num_sms()) * 4));
+    p2p_reduce_kernel<<<std::max(grid, 1), 256, 0, stream>>>(peers, n_ranks, step, sf, kf, stats_out, k_rand_out);
+    VQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int vq_p2p_exchange(void* const* regions, int n_ranks, int rank, unsigned int step, int k_bins, int emb_width,
+                    float* stats_out, float* k_rand_out, void* stream) {
+    if (vq_p2p_publish(regions, n_ranks, rank, step, stream)) return 1;
+    return vq_p2p_collect(regions, n_ranks, rank, step, k_bins, emb_width, stats_out, k_rand_out, stream);
 }
 
 int vq_restart_rows_device(const float* x, const float* mask, int64_t N, int64_t D, int64_t T, int K, uint64_t seed,

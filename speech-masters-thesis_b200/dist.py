@@ -130,14 +130,24 @@ class PeerExchange:
         self.step += 1
         return self._slots[self.step & 1]
 
-    def exchange(self, stream):
-        """Publish this rank's slots of the current step, wait for all peers, return (summed statistics, rank 0's restart rows)
-        -- buffers owned by this object, valid until the exchange after next."""
+    def publish(self, stream):
+        """Tell every peer that this rank's slots of the current step are complete (enqueue right after K3a / the restart rows,
+        BEFORE K2: the peers' flags then arrive while K2 runs)."""
         from ._lib import check
+        with torch.cuda.device(self.device):
+            check(self.lib.vq_p2p_publish(self.regions, self.n_ranks, self.rank, self.step, stream), "vq_p2p_publish")
+        self._published = self.step
+
+    def collect(self, stream):
+        """Wait for all peers' flags of the current step, return (statistics summed in rank order, rank 0's restart rows) --
+        buffers owned by this object, valid until the collect after next."""
+        from ._lib import check
+        if getattr(self, "_published", 0) != self.step:
+            self.publish(stream)
         stats, k_rand = self._outs[self.step & 1]
         with torch.cuda.device(self.device):
-            check(self.lib.vq_p2p_exchange(self.regions, self.n_ranks, self.rank, self.step, self.k_bins, self.emb_width,
-                                           stats.data_ptr(), k_rand.data_ptr(), stream), "vq_p2p_exchange")
+            check(self.lib.vq_p2p_collect(self.regions, self.n_ranks, self.rank, self.step, self.k_bins, self.emb_width,
+                                          stats.data_ptr(), k_rand.data_ptr(), stream), "vq_p2p_collect")
         return stats, k_rand
 
 

@@ -366,6 +366,9 @@ class BottleneckBlock(nn.Module):
             pending = dict(stats=stats, k_rand=k_rand, work=None, x=x, mask=mask, peer=peer, k_slot=k_slot)
             if k_rand is None and not self.rng_parity:
                 pending["k_rand"] = self._restart_rows_nct(x, mask)        # device-side draw: no host sync
+            if pending["k_rand"] is not None and peer is not None:
+                k_slot.copy_(pending["k_rand"])                            # (only rank 0's rows are read by the peers)
+                peer.publish(_stream(x))                                   # before K2: the peers' latency hides behind it
             if pending["k_rand"] is not None and peer is None:
                 # reference: broadcast(k_rand) + all_reduce(k_sum) + all_reduce(k_elem) (bottleneck.py:73-75);
                 # here ONE all-reduce of the packed buffer (see dist.py), overlapped with K2
@@ -382,8 +385,9 @@ class BottleneckBlock(nn.Module):
                 if peer is None:
                     k_rand, pending["work"] = dist.allreduce_statistics(stats, k_rand, kk, d, async_op=True)
             if peer is not None:
-                pending["k_slot"].copy_(k_rand)                              # (only rank 0's rows are read by the peers)
-                stats, k_rand = peer.exchange(_stream(x))                    # publish, wait for the peers, sum in rank order
+                if pending["k_rand"] is None:                                # (rng_parity: the rows only exist now)
+                    pending["k_slot"].copy_(k_rand)
+                stats, k_rand = peer.collect(_stream(x))                     # (publish if not done,) wait for the peers, sum in rank order
             elif pending["work"] is not None:
                 pending["work"].wait()                                       # the current stream waits for the collective
             k_new = torch.empty_like(self.k)
