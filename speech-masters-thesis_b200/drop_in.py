@@ -5,7 +5,8 @@
 After this, ``models.vqvae.bottleneck.{BottleneckBlock, Bottleneck, NoBottleneck, NoBottleneckBlock}`` are
 the classes of this package, so ``models/vqvae/vqvae.py:74-79``, ``scripts/generate_vq_dataset.py:69,75`` and
 ``models/transformer_lm/transformer_lm.py:96-103`` pick them up unchanged.  State dict keys are identical
-(``bottleneck.level_blocks.<i>.k``), so existing checkpoints load.
+(``bottleneck.level_blocks.<i>.k``), so existing checkpoints load.  ``models.vqtts.bottleneck.Bottleneck`` (the grouped,
+phoneme-conditioned quantiser; vqtts/bottleneck.py:7-77) becomes ``GroupedBottleneck`` when that module is importable.
 """
 import importlib
 import sys
@@ -23,4 +24,13 @@ def patch_reference(module_name: str = "models.vqvae.bottleneck"):
         for name in ("BottleneckBlock", "Bottleneck", "NoBottleneckBlock", "NoBottleneck"):
             if hasattr(other, name):
                 setattr(other, name, getattr(quantizer, name))
+    # the grouped quantiser lives in its own module under the same class name `Bottleneck`
+    if module_name == "models.vqvae.bottleneck":
+        try:
+            tts = sys.modules.get("models.vqtts.bottleneck") or importlib.import_module("models.vqtts.bottleneck")
+        except ImportError:
+            tts = None
+        if tts is not None:
+            tts.BottleneckBlock = quantizer.BottleneckBlock
+            tts.Bottleneck = quantizer.GroupedBottleneck
     return mod

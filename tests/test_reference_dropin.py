@@ -60,6 +60,27 @@ def test_patch_reference_inside_the_real_vqvae_cpu():
             ours(x, torch.tensor([128 * 8]))
 
 
+@needs_ref
+def test_patch_reference_covers_the_grouped_tts_quantiser():
+    """models/vqtts/bottleneck.py::Bottleneck (same class name, other module) becomes GroupedBottleneck."""
+    import vqb200
+    bott, vqv = _fresh_reference_modules()
+    tts = importlib.import_module("models.vqtts.bottleneck")
+    saved = {n: getattr(bott, n) for n in REF_CLASSES}
+    saved_tts = (tts.Bottleneck, tts.BottleneckBlock)
+    try:
+        vqb200.patch_reference()
+        assert tts.Bottleneck is vqb200.GroupedBottleneck and tts.BottleneckBlock is vqb200.BottleneckBlock
+        assert vqv.Bottleneck is vqb200.Bottleneck                                    # the VQ-VAE wrapper is not clobbered
+        blk = tts.Bottleneck(n_vocab=5, l_bins=8, emb_width=16, mu=0.99, threshold=1.0)
+        assert blk.k.shape == (40, 16) and list(blk.state_dict().keys()) == ["k"]
+    finally:
+        tts.Bottleneck, tts.BottleneckBlock = saved_tts
+        for n, c in saved.items():
+            setattr(bott, n, c)
+            setattr(vqv, n, c) if hasattr(vqv, n) else None
+
+
 def _seed_codebooks(ref, ours, dev, gen):
     K, D = ref.bottleneck.level_blocks[0].k.shape
     code = torch.randn(K, D, generator=gen) * 0.05
