@@ -317,12 +317,14 @@ def run_b200(args):
     lib.vq_host_ctx_destroy(ctx)
 
     # whole training-mode forward of the module on every rank (K1 + K3a + {ONE all-reduce || K2} + K3b + restart-row glue)
-    def timed_all(fn, reps=5):
-        for _ in range(2):
+    def timed_all(fn, reps=5, rounds=3):
+        for _ in range(3):
             fn()
         barrier()
         best = 1e9
-        for _ in range(3):                       # `reps` back-to-back forwards per measurement: launches overlap execution
+        for _ in range(rounds):                  # `reps` back-to-back forwards per measurement: launches overlap execution
+            if world > 1:
+                barrier()                        # all ranks start a measurement together
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(reps):
@@ -339,9 +341,11 @@ def run_b200(args):
         dist.broadcast(k0, 0)                 # one codebook for all replicas (every rank's synthetic batch has its own)
     blk.k, blk.k_sum, blk.k_elem, blk.init = k0, k0.clone() * 4, torch.full((K_BINS,), 4.0, device=dev), True
     blk.train()
-    fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
+    fwd_ms = timed_all(lambda: blk(xd, md_all, update_k=True), reps=10)
     blk.rng_parity = False                   # restart rows drawn on the device: no host sync, no CPU randperm
-    fwd_fast_ms = timed_all(lambda: blk(xd, md_all, update_k=True))
+    # 20 back to back, best of 5: with fewer, the start-up skew between the ranks (each leaves its own synchronize at its own
+    # time, and a step cannot finish before the slowest rank has published its statistics) dominates a 0.35 ms step
+    fwd_fast_ms = timed_all(lambda: blk(xd, md_all, update_k=True), reps=20, rounds=5)
     # replicas must still be bit-identical after all those all-reduced updates (bottleneck.py:72-75)
     replicas_identical = None
     if world > 1:
@@ -366,7 +370,7 @@ def run_b200(args):
         graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(graph):
             g_out = blk(xd, md_all, update_k=True)
-        fwd_graph_ms = timed_all(graph.replay)
+        fwd_graph_ms = timed_all(graph.replay, reps=20, rounds=5)
         del graph, g_out
     except Exception:                                          # noqa: BLE001  (reported as null, never fatal for the bench line)
         fwd_graph_ms = None

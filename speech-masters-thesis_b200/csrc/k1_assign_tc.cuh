@@ -64,6 +64,7 @@ constexpr int A_BUFS_MAX = 4;                // remaining TMEM columns: up to fo
 constexpr int CD = 4;                        // depth of the candidate / row-statistics hand-off between scan and back stage
 constexpr uint32_t SPIN_LIMIT = 1u << 24;    // a lost barrier traps (after seconds) instead of hanging the GPU
 constexpr uint32_t WAIT_HINT_NS = 2000;
+constexpr int HN_STREAM_BYTES = 8 * 2 * 128 * 4;   // 8 scan warps x 2 buffers x 128 offsets
 constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared memory up to this many (padded) codes
 
 struct Params {
@@ -74,6 +75,7 @@ struct Params {
     int N, D, Dp, K, Kp, T;
     int tiles_per_utt, n_tiles, n_nt, n_kb, n_xch, a_bufs, acc_stages, lag, resident, b_stages, vec_k;
     int hn_in_smem;
+    int hn_stream;            // offsets neither folded nor resident: every scan warp stages its next code tile's 128 offsets itself
     int fold;                // -(||e||^2/2 - B) rides in the MMA as one extra k-step (resident codebooks only): no FADD, no loads in the scan
     int pair;                // even number of code tiles: MMAs are issued with N = 256 over two adjacent B tiles
     int cd;                  // depth of the scan -> back-stage hand-off (<= CD)
@@ -993,6 +995,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         Ring rs;                                              // accumulator stage of code tile qa (2 or 3 stages)
         const uint32_t acc_stages = uint32_t(p.acc_stages);
         const uint32_t gap_cap = HARD ? ctl->gap_cap : 0u;     // best - runner-up above this many ulps: safe whatever the frame's norm
+        // streamed offsets: this warp's two 128-float buffers, the group's NEXT code tile always in flight (cp.async)
+        auto stage_offsets = [&](int nt_, uint32_t buf) {     // 16 bytes per lane, global -> shared without a register in between
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(hn_s + (warp - 4) * 256 + buf + lane * 4)),
+                         "l"(p.hn_off + size_t(nt_) * TN + lane * 4) : "memory");
+        };
+        if (p.hn_stream && wg < p.n_nt) stage_offsets(wg, 0u);
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, rc.next(uint32_t(p.cd))) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
@@ -1004,6 +1012,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
                 if ((uint32_t(nt) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
+                // buffer of this warp's pair (as a float offset, 0 or TN): parity of the number of code tiles this group has scanned
+                const uint32_t hbuf = p.hn_stream ? ((it * uint32_t((p.n_nt - wg + 1) >> 1) + uint32_t(nt >> 1)) & 1u) * uint32_t(TN) : 0u;
+                if (p.hn_stream) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");               // this tile's offsets (issued one tile ago) have landed
+                    __syncwarp();                                                  // ... for every lane, and the other buffer is no longer read
+                    stage_offsets(nt + 2 < p.n_nt ? nt + 2 : wg, hbuf ^ uint32_t(TN));       // (wraps to the next frame tile's first code tile)
+                }
                 // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
                 // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
                 mbar_wait_backoff(smem_u32(&ctl->acc_full[s]), sph, p.scan_sleep_ns);
@@ -1041,6 +1056,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     int blk;
                     if (p.fold) scan64<2>(v0, v1, nullptr, ch, t1, t2, blk);
                     else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, ch, t1, t2, blk);
+                    else if (p.hn_stream) scan64<1>(v0, v1, hn_s + (warp - 4) * 256 + hbuf + half * 64, ch, t1, t2, blk);
                     else scan64<0>(v0, v1, p.hn_off + cbase, ch, t1, t2, blk);
 #endif
                     // fold this half tile into the running pair: r1 = best key, r2 = best key outside the winner's block
@@ -1168,6 +1184,12 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
         if (smem_base + handoff_bytes(CD) + size_t(Kp) * 4 <= budget) p.hn_in_smem = 1;
         else if (smem_base + handoff_bytes(3) + size_t(Kp) * 4 <= budget) { p.hn_in_smem = 1; p.cd = 3; }
     }
+    // Large codebooks (neither folded nor resident offsets): each of the 8 scan warps double-buffers the 128 offsets of its
+    // next code tile in 1 KB of shared memory, loaded a whole tile ahead.  (Reading them from global memory inside the scan
+    // exposed an L2 round trip per half tile -- with 227 KB of shared memory carved out the L1 holds next to nothing:
+    // 1.05 us instead of 0.63 us per code tile, measured at K = 8192 vs 4096.)
+    p.hn_stream = (!p.fold && !p.hn_in_smem) ? 1 : 0;
+    if (p.hn_stream && smem_base + handoff_bytes(p.cd) + HN_STREAM_BYTES > budget) p.cd = 3;
     // Three accumulator stages of N = 128 (the tensor core never waits for a scan group to read a stage out) when TMEM
     // can still hold two converted tiles next to them; the constant operand of the folded step then comes from shared memory.
     // Measured against the two-stage N = 256 mode (K = 512): 3 % faster at D = 128 on the LJSpeech-like batch (0.0690 vs 0.0713 ms),
@@ -1189,7 +1211,8 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.lag = std::min(p.a_bufs, p.cd - 1);                       // the back stage trails the front stage by this many tiles
     p.scan_sleep_ns = tc_env().scan_sleep >= 0 ? uint32_t(tc_env().scan_sleep) : 64u;   // (0 .. 250 ns measured within 1 % of each other)
     smem = smem_base + handoff_bytes(p.cd) +
-           (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES + (p.const_smem ? ACONST_BYTES : 0) : (p.hn_in_smem ? size_t(Kp) * 4 : 0));
+           (p.fold ? size_t(p.n_nt) * HN_TILE_BYTES + (p.const_smem ? ACONST_BYTES : 0)
+                   : (p.hn_in_smem ? size_t(Kp) * 4 : (p.hn_stream ? HN_STREAM_BYTES : 0)));
     if (smem > budget) return "shared memory budget exceeded";
     return nullptr;
 }
