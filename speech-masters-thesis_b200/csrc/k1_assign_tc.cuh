@@ -83,6 +83,7 @@ struct Params {
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
     int x_cpasync;           // x tiles by cp.async (any T / alignment) instead of TMA
     int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
+    int fwait_mode;          // how the front group waits for a free A buffer / a landed x stage (3: suspending wait + 500 / 64 ns sleeps)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
 };
@@ -825,7 +826,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const uint32_t cb = rfin.i, cph = rfin.ph;
             rfin.next(uint32_t(p.cd));
             if (wq == 0) VQ_TRACE(6, j);
-            mbar_wait<500>(smem_u32(&ctl->cand_full[cb]), cph);
+            if (p.fwait_mode == 3) mbar_wait<500>(smem_u32(&ctl->cand_full[cb]), cph);
+            else mbar_wait_mode(smem_u32(&ctl->cand_full[cb]), cph, p.fwait_mode);
             if (wq == 0) VQ_TRACE(7, j);
             const Cand ca = cand[(cb * 2 + 0) * TM + r], cc = cand[(cb * 2 + 1) * TM + r];
             const float2 st = rowstat[cb * TM + r];
@@ -836,7 +838,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             bool unsafe = false;
             uint32_t cand_mask = 0xFFFFFFFFu;                 // bits 0-15: residue chains of scan group 0 (even code tiles), 16-31: group 1
             const int64_t row = int64_t(n) * p.T + t;
+#if VQ_EXPERIMENT & 256                   /* timing experiment: the back stage only shakes hands and stores a candidate */
+            if (in_tile) p.idx[row] = ca.c1 + int(st.x != 1.25f ? 0 : cc.c1);
+            if (false) {
+#else
             if (in_tile) {
+#endif
                 const float xx = st.x, rr = st.y;
                 const bool a_wins = ca.k1 >= cc.k1;
                 const int c1 = a_wins ? ca.c1 : cc.c1;
@@ -928,7 +935,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         Ring ra, rstat;                                       // A buffer being filled; row-statistics slot of this tile
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, ra.next(uint32_t(p.a_bufs)), rstat.next(uint32_t(p.cd))) {
             const uint32_t a = ra.i, aph = ra.ph;
-            mbar_wait<500>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
+            if (p.fwait_mode == 3) mbar_wait<500>(smem_u32(&ctl->a_empty[a]), aph ^ 1);
+            else mbar_wait_mode(smem_u32(&ctl->a_empty[a]), aph ^ 1, p.fwait_mode);
             tc_fence_after();
             if (wq == 0) VQ_TRACE(3, it);
             const uint32_t a_tmem = tmem + lane_base + a_col0 + a * a_stride;
@@ -937,7 +945,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             float xa[4] = {0.f, 0.f, 0.f, 0.f}, ra4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int ch = 0; ch < p.n_xch; ++ch, ++qx) {
                 const uint32_t s = qx % XS, ph = (qx / XS) & 1;
-                mbar_wait<64>(smem_u32(&ctl->x_full[s]), ph);
+                if (p.fwait_mode == 3) mbar_wait<64>(smem_u32(&ctl->x_full[s]), ph);
+                else mbar_wait_mode(smem_u32(&ctl->x_full[s]), ph, p.fwait_mode);
                 if (wq == 0 && ch == 0) VQ_TRACE(4, it);
                 const XT* xs = reinterpret_cast<const XT*>(xs_base + s * X_STAGE_BYTES) + r;
                 uint32_t pk[16];
@@ -1040,6 +1049,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     tc_ld32(taddr + 96, v[3]);
                     tc_wait_ld();
 #endif
+                    // (Releasing the stage only after the first half has been scanned, with the second half still in flight, was
+                    //  measured equal on speech-like and 1.6 % slower on Gaussian latents: ptxas already gives every LDTM its own
+                    //  scoreboard, so the scan of the first columns starts as soon as THEY have landed either way.)
                     tc_fence_before();
                     mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                // all 128 columns are in registers: free the stage
                     if (warp == 4) VQ_TRACE_NT(13, it, nt);
@@ -1050,10 +1062,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     const uint32_t (&v0)[32] = v[2 * half];
                     const uint32_t (&v1)[32] = v[2 * half + 1];
                     uint32_t t1, t2;
+                    int blk = 0;
 #if VQ_EXPERIMENT & 1                     /* timing experiment: no scan arithmetic */
                     t1 = v0[0] ^ v1[31]; t2 = v0[31] ^ v1[0];
+#if VQ_EXPERIMENT & 512                   /* ... but the warp stays away for about as long (no issue slots used) */
+                    __nanosleep(200);
+#endif
 #else
-                    int blk;
                     if (p.fold) scan64<2>(v0, v1, nullptr, ch, t1, t2, blk);
                     else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, ch, t1, t2, blk);
                     else if (p.hn_stream) scan64<1>(v0, v1, hn_s + (warp - 4) * 256 + hbuf + half * 64, ch, t1, t2, blk);
@@ -1137,7 +1152,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
 // VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, hard = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, hard = -1, fwait = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
@@ -1145,6 +1160,7 @@ struct TcEnv {
         if (const char* e = getenv("VQ_K1_SCAN_SLEEP")) scan_sleep = atoi(e);
         if (const char* e = getenv("VQ_K1_PIPE")) pipe = atoi(e);
         if (const char* e = getenv("VQ_K1_AWAIT")) await = atoi(e);
+        if (const char* e = getenv("VQ_K1_FWAIT")) fwait = atoi(e);
         if (const char* e = getenv("VQ_K1_HARD")) hard = atoi(e);
     }
 };
@@ -1204,6 +1220,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
     p.await_mode = tc_env().await >= 0 ? tc_env().await : 0;
+    p.fwait_mode = tc_env().fwait >= 0 ? tc_env().fwait : 3;
     p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)
     const int a_cols = ((p.fold && !p.const_smem) ? p.a_const_col : 512) - p.acc_stages * TN;
     p.a_bufs = std::min(A_BUFS_MAX, a_cols / (Dp / 2));          // converted tiles that fit the remaining TMEM columns

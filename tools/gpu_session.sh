@@ -1,6 +1,6 @@
 #!/bin/bash
-# large-K offsets staged per scan warp: parity first, then the sweep
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_audit.py -m gpu -x -q -k "sweep_corner or tcgen05_route or bf16" 2>&1 | tail -4
-timeout 1200 python tools/sweep.py > gpurun_out/sweep.log 2>&1; echo "sweep rc=$?"; tail -3 gpurun_out/sweep.log | cut -c1-300
-timeout 600 python tools/sweep.py --gaussian --quick > gpurun_out/sweepg.log 2>&1; echo "sweepg rc=$?"
+timeout 600 python -m pytest tests/test_gpu_audit.py -m gpu -x -q -k "every_row or sweep_corner" 2>&1 | tail -3
+python tools/ab_k1.py ab/libvqb200_e0.so ab/libvqb200_e1024.so ab/libvqb200_e2048.so ab/libvqb200_e3072.so 2>&1 | tail -1 | tee gpurun_out/experiment_scan.log
+python tools/ab_k1.py ab/libvqb200_e0.so ab/libvqb200_e3072.so gaussian 2>&1 | tail -1 | tee -a gpurun_out/experiment_scan.log
+python tools/tc_timeline.py > gpurun_out/tl.log 2>&1; tail -33 gpurun_out/tl.log | head -12
