@@ -146,7 +146,7 @@ assign_simt_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T,
 // ------------------------------------------------------------------------------------------------
 // Exact re-scan of the frames the tcgen05 kernel could not prove safe (bottleneck.py:129-134 for those rows, FP32, lowest
 // index on ties like torch.min).  The tcgen05 pass leaves, per listed frame, a 32-bit mask: bit (16 g + j) set means "the
-// exact winner may be a code of scan group g (code tile parity) in residue chain j (code % 16 == j)"; every other code was
+// exact winner may be a code of scan group g (group of code tile nt = (nt >> own_shift) & 1) in residue chain j (code % 16 == j)"; every other code was
 // proven out of reach by its FP16 score (see finish() in k1_assign_tc.cuh).  Typically two chains survive: K/16 codes
 // instead of K -- the re-scan of 2 % of a batch went from 0.11 ms (all codes, 128-row tiles, 64-bit atomics) to ~0.01 ms.
 //   one WARP per listed frame; the frame's D values live in registers (lane = depth quad), a candidate code row is one
@@ -206,12 +206,13 @@ __device__ __forceinline__ float list_reduce8(float (&part)[8], int lane) {
     return part[0];
 }
 // walks the (group, chain, code tile) segments a mask selects, in increasing group / chain / tile order
+// (own_shift: scan group of code tile nt = (nt >> own_shift) & 1, see plan_assign_tc)
 struct ListWalk {
     uint32_t mask;
-    int n_code_tiles, g, res, nt;
-    __device__ __forceinline__ ListWalk(uint32_t m, int n) : mask(m), n_code_tiles(n), g(-1), res(0), nt(1 << 30) {}
+    int n_code_tiles, g, res, nt, sh;
+    __device__ __forceinline__ ListWalk(uint32_t m, int n, int own_shift) : mask(m), n_code_tiles(n), g(-1), res(0), nt(1 << 30), sh(own_shift) {}
     __device__ __forceinline__ bool next() {
-        nt += 2;
+        nt += sh ? ((nt & 1) ? 3 : 1) : 2;                 // the group's next code tile
         while (nt >= n_code_tiles) {
             // next chain of this group, else the next group
             uint32_t mg = g >= 0 ? (mask >> (16 * g)) & 0xFFFFu & ~((2u << res) - 1u) : 0u;
@@ -222,7 +223,7 @@ struct ListWalk {
                 if (mg) break;
             }
             res = __ffs(mg) - 1;
-            nt = g;
+            nt = g << sh;                                      // the group's first code tile
         }
         return true;
     }
@@ -234,7 +235,7 @@ struct ListWalk {
 template <bool VEC, int MAXQ, typename XT>
 __global__ void __launch_bounds__(L_WARPS * 32)
 assign_list_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
-                   const float* __restrict__ ee, int K, int n_code_tiles, int64_t* __restrict__ idx, float* __restrict__ min_d,
+                   const float* __restrict__ ee, int K, int n_code_tiles, int own_shift, int64_t* __restrict__ idx, float* __restrict__ min_d,
                    double* __restrict__ scalars, const int* __restrict__ row_list, const uint32_t* __restrict__ row_mask,
                    AssignHeader* __restrict__ hdr, unsigned int* hard_hint) {
     __shared__ double red[32];
@@ -268,7 +269,7 @@ assign_list_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T, const 
         xx = warp_sum(xx);
         float bd = inf;
         int bi = 0x7fffffff;
-        ListWalk walk(mask, n_code_tiles);
+        ListWalk walk(mask, n_code_tiles, own_shift);
         while (walk.next()) {
             const int nt0 = walk.nt, res0 = walk.res;
             const bool two = walk.next();

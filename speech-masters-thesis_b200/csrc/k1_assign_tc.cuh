@@ -83,6 +83,7 @@ struct Params {
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
     int x_cpasync;           // x tiles by cp.async (any T / alignment) instead of TMA
     int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
+    int own_shift;           // scan group of code tile nt = (nt >> own_shift) & 1: 0 = alternate tiles, 1 = alternate PAIRS of tiles
     int fwait_mode;          // how the front group waits for a free A buffer / a landed x stage (3: suspending wait + 500 / 64 ns sleeps)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
     int const_smem;          // that slice lives in shared memory instead (SS-mode MMA for the folded step): frees TMEM for a 3rd accumulator stage
@@ -623,13 +624,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     auto steady = [&](auto nkb_tag) {
                         constexpr int NJ = 4 * decltype(nkb_tag)::value;          // MMAs per batch (without the folded step)
                         int nt = 0, tile_c = tile;
-                        uint32_t a_tmem_c = a_tmem;
+                        uint32_t a_tmem_c = a_tmem, it_c = it;
                         mbar_spin(smem_u32(&ctl->acc_empty[rs.i]), rs.ph ^ 1);
                         tc_fence_after();
                         for (;;) {
                             const uint32_t st = rs.i;
                             const uint32_t d_tmem = tmem + st * TN;
                             const uint64_t b = bd0 + uint64_t(nt) * uint64_t(B_STAGE_BYTES >> 4);
+                            VQ_TRACE_NT(10, it_c, nt);
                             if (leader) issue_part<0, NJ - 2, IDESC>(d_tmem, a_tmem_c, b, kb_stride);
                             // ---- the next batch: which tile / A buffer / accumulator stage, and wait for them
                             Ring rs_n = rs, ra_n = ra;
@@ -661,7 +663,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                 if (last) tc_commit(smem_u32(&ctl->a_empty[ra.i]));
                             }
                             __syncwarp();
+                            VQ_TRACE_NT(11, it_c, nt);
                             if (!more) break;
+                            if (last) ++it_c;
                             rs = rs_n; ra = ra_n; nt = nt_n; tile_c = tile_n; a_tmem_c = a_tmem_n;
                         }
                     };
@@ -1018,8 +1022,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             for (int j = 0; j < 16; ++j) ch[j] = 0u;
             for (int nt = 0; nt < p.n_nt; ++nt, ++qa, rs.next(acc_stages)) {
                 // The two scan groups take ALTERNATE code tiles (group 0 the even ones), so one group's TMEM loads and barrier
-                // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together.
-                if ((uint32_t(nt) & 1u) != uint32_t(wg)) continue;
+                // waits overlap the other group's arithmetic on the same scheduler instead of both stalling together -- or, with
+                // four code tiles and three accumulator stages, alternate PAIRS (see plan_assign_tc).
+                if (((uint32_t(nt) >> p.own_shift) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
                 // buffer of this warp's pair (as a float offset, 0 or TN): parity of the number of code tiles this group has scanned
                 const uint32_t hbuf = p.hn_stream ? ((it * uint32_t((p.n_nt - wg + 1) >> 1) + uint32_t(nt >> 1)) & 1u) * uint32_t(TN) : 0u;
@@ -1033,7 +1038,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 mbar_wait_backoff(smem_u32(&ctl->acc_full[s]), sph, p.scan_sleep_ns);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
-                if (warp == 4) VQ_TRACE_NT(12, it, nt);
+                if (warp == 4 || warp == 8) VQ_TRACE_NT(12, it, nt);
                 uint32_t v[4][32];
                 {
                     const uint32_t taddr = tmem + lane_base + s * TN;
@@ -1054,7 +1059,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     //  scoreboard, so the scan of the first columns starts as soon as THEY have landed either way.)
                     tc_fence_before();
                     mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                // all 128 columns are in registers: free the stage
-                    if (warp == 4) VQ_TRACE_NT(13, it, nt);
+                    if (warp == 4 || warp == 8) VQ_TRACE_NT(13, it, nt);
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -1083,7 +1088,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         r2 = max(r2, t1);
                     }
                 }
-                if (warp == 4) VQ_TRACE_NT(14, it, nt);
+                if (warp == 4 || warp == 8) VQ_TRACE_NT(14, it, nt);
             }
             const uint32_t cb = rc.i, cph = rc.ph;
             mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
@@ -1112,6 +1117,17 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         }
     } else {
         reg_dec<REGS_ISSUER>();                                     // W_ALLOC: idle until the end
+        // (timeline runs only: this warp watches the accumulator barriers of CTA 0 with a non-suspending probe and records when
+        //  every MMA batch really completes -- the scan groups' own time stamps include their wake-up latency)
+        if (p.trace && blockIdx.x == 0 && p.n_nt == 4 && p.trace_tiles == 32 && !p.pair) {
+            Ring rs;
+            uint32_t it = 0;
+            for (int tile = first; tile < p.n_tiles; tile += step, ++it)
+                for (int nt = 0; nt < p.n_nt; ++nt, rs.next(uint32_t(p.acc_stages))) {
+                    mbar_spin(smem_u32(&ctl->acc_full[rs.i]), rs.ph);
+                    VQ_TRACE_NT(15, it, nt);
+                }
+        }
     }
 
     tc_fence_before();
@@ -1152,7 +1168,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Measurement switches, read ONCE per process (never set in production): VQ_K1_FOLD=0, VQ_K1_STAGES=2|3, VQ_K1_PAIR=0,
 // VQ_K1_SCAN_SLEEP=<ns>.  -1 = not set.
 struct TcEnv {
-    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, hard = -1, fwait = -1;
+    int fold = -1, stages = -1, pair = -1, scan_sleep = -1, pipe = -1, await = -1, hard = -1, fwait = -1, own = -1;
     TcEnv() {
         if (const char* e = getenv("VQ_K1_FOLD")) fold = atoi(e);
         if (const char* e = getenv("VQ_K1_STAGES")) stages = atoi(e);
@@ -1161,6 +1177,7 @@ struct TcEnv {
         if (const char* e = getenv("VQ_K1_PIPE")) pipe = atoi(e);
         if (const char* e = getenv("VQ_K1_AWAIT")) await = atoi(e);
         if (const char* e = getenv("VQ_K1_FWAIT")) fwait = atoi(e);
+        if (const char* e = getenv("VQ_K1_OWN")) own = atoi(e);
         if (const char* e = getenv("VQ_K1_HARD")) hard = atoi(e);
     }
 };
@@ -1219,6 +1236,13 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     p.pair = (p.n_nt % 2 == 0) ? 1 : 0;                        // even number of code tiles: MMAs are issued with N = 256
     if (tc_env().pair >= 0) p.pair = p.pair && tc_env().pair != 0;
     if (p.acc_stages != 2) p.pair = 0;
+    // Which scan group reads which code tile.  Alternating tiles puts each group's per-frame hand-off (reductions, slot
+    // hand-shake, loop overhead: ~1200 cycles) between its last code tile of frame tile i and its first of i + 1, and with
+    // three accumulator stages the tensor core then waits ~900 cycles per frame tile for that first stage to be read out
+    // (tools/tc_timeline.py).  With exactly four code tiles, group 0 takes tiles 0-1 and group 1 tiles 2-3: each group's
+    // hand-off falls into the two batches the tensor core runs for the OTHER group.
+    p.own_shift = (p.acc_stages == 3 && p.n_nt == 4) ? 1 : 0;
+    if (tc_env().own >= 0 && p.own_shift) p.own_shift = tc_env().own != 0 ? 1 : 0;     // VQ_K1_OWN=0: alternate tiles (A/B switch)
     p.await_mode = tc_env().await >= 0 ? tc_env().await : 0;
     p.fwait_mode = tc_env().fwait >= 0 ? tc_env().fwait : 3;
     p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)

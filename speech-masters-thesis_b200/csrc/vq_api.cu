@@ -209,11 +209,17 @@ static int assign_impl(const XT* x, int64_t N, int64_t D, int64_t T, const float
         cfg.numAttrs = (g_prof.on && pslot >= 0) ? 0 : 1;          // (event records between the two kernels serialise them anyway)
         const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0);
         const int n_code_tiles = w.Kp / 128;
+        int own_shift = 0;                                     // how the main kernel assigned code tiles to its two scan groups
+        {
+            tc::Params plan;
+            size_t plan_smem = 0;
+            if (plan_assign_tc(int(D), K, plan, plan_smem) == nullptr) own_shift = plan.own_shift;
+        }
         int dev = 0;
         VQ_CUDA_OK(cudaGetDevice(&dev));
         unsigned int* hint_dev = hard_hint(dev);               // (unified addressing: the mapped host pointer is valid on the device)
         auto launch_list = [&](auto kernel) {
-            return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, idx, min_d, scalars,
+            return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, own_shift, idx, min_d, scalars,
                                       (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr, hint_dev);
         };
         if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1, XT>));

@@ -43,7 +43,7 @@ def main(n_utt=256, K=512, D=128):
         vals = [int(tr[e, i]) - t0 if int(tr[e, i]) else -1 for e in range(10)]
         rows.append(vals)
         print(f"{i:4d} " + " ".join(f"{v:12d}" for v in vals))
-    print("per code-tile probes, local tiles 8..15: mma_go(after acc_empty)  mma_commit  scan_go(after acc_full)  scan_released  scan_done  mma_done_seen_by_issuer")
+    print("per code-tile probes, local tiles 8..15: mma_go(after acc_empty)  mma_commit  scan_go(after acc_full)  scan_released  scan_done  mma_done(observer warp / issuer probe)")
     fine = []
     for q in range(32):
         vals = [int(tr[e, q]) - t0 if int(tr[e, q]) else -1 for e in range(10, 16)]
