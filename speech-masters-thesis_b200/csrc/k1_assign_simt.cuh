@@ -207,11 +207,25 @@ __device__ __forceinline__ float list_reduce8(float (&part)[8], int lane) {
 }
 // walks the (group, chain, code tile) segments a mask selects, in increasing group / chain / tile order
 // (own_shift: scan group of code tile nt = (nt >> own_shift) & 1, see plan_assign_tc)
+// tiles: per group, the 24-bit map of its code tiles that can hold the winner (bit = (own index * scale) >> 16, as in the main kernel)
 struct ListWalk {
     uint32_t mask;
+    uint2 tiles;
+    uint32_t scale;
     int n_code_tiles, g, res, nt, sh;
-    __device__ __forceinline__ ListWalk(uint32_t m, int n, int own_shift) : mask(m), n_code_tiles(n), g(-1), res(0), nt(1 << 30), sh(own_shift) {}
+    __device__ __forceinline__ ListWalk(uint32_t m, uint2 t, uint32_t sc, int n, int own_shift)
+        : mask(m), tiles(t), scale(sc), n_code_tiles(n), g(-1), res(0), nt(1 << 30), sh(own_shift) {}
+    __device__ __forceinline__ bool tile_flagged() const {
+        const uint32_t oi = sh ? ((uint32_t(nt) >> 2) << 1 | (uint32_t(nt) & 1u)) : (uint32_t(nt) >> 1);
+        return (((g ? tiles.y : tiles.x) >> ((oi * scale) >> 16)) & 1u) != 0u;
+    }
     __device__ __forceinline__ bool next() {
+        for (;;) {
+            if (!step()) return false;
+            if (tile_flagged()) return true;
+        }
+    }
+    __device__ __forceinline__ bool step() {
         nt += sh ? ((nt & 1) ? 3 : 1) : 2;                 // the group's next code tile
         while (nt >= n_code_tiles) {
             // next chain of this group, else the next group
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(L_WARPS * 32)
 assign_list_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T, const float* __restrict__ k,
                    const float* __restrict__ ee, int K, int n_code_tiles, int own_shift, int64_t* __restrict__ idx, float* __restrict__ min_d,
                    double* __restrict__ scalars, const int* __restrict__ row_list, const uint32_t* __restrict__ row_mask,
-                   AssignHeader* __restrict__ hdr, unsigned int* hard_hint) {
+                   const uint2* __restrict__ row_tiles, uint32_t tile_scale, AssignHeader* __restrict__ hdr, unsigned int* hard_hint) {
     __shared__ double red[32];
     __shared__ bool is_last;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // nothing the tcgen05 kernel wrote may be read before this
@@ -269,7 +283,7 @@ assign_list_kernel(const XT* __restrict__ x, int64_t N, int D, int64_t T, const 
         xx = warp_sum(xx);
         float bd = inf;
         int bi = 0x7fffffff;
-        ListWalk walk(mask, n_code_tiles, own_shift);
+        ListWalk walk(mask, row_tiles[j], tile_scale, n_code_tiles, own_shift);
         while (walk.next()) {
             const int nt0 = walk.nt, res0 = walk.res;
             const bool two = walk.next();

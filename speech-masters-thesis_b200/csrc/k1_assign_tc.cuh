@@ -30,6 +30,7 @@
 // which proves it is the exact-arithmetic argmax; every other frame goes to a worklist that the exact FP32 kernel
 // (k1_assign_simt.cuh, LIST mode) re-scans.  The output therefore never depends on reduced-precision arithmetic.
 #pragma once
+#include <cstddef>
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -69,7 +70,7 @@ constexpr int HN_SMEM_MAX = 4096;            // ||e||^2/2 - B staged in shared m
 
 struct Params {
     const void* x; const float* k; const float* ee; const float* hn; const float* hn_off;
-    AssignHeader* hdr; int* unsafe_rows; uint32_t* unsafe_mask;
+    AssignHeader* hdr; int* unsafe_rows; uint32_t* unsafe_mask; uint2* unsafe_tiles;
     int64_t* idx; float* min_d; double* scalars; float* dbg;
     long long* trace; int trace_tiles;     // optional per-role clock64 timeline of CTA 0 (audit calls only)
     int N, D, Dp, K, Kp, T;
@@ -83,6 +84,7 @@ struct Params {
     uint32_t scan_sleep_ns;  // back-off of the scan groups between probes of the accumulator barrier
     int x_cpasync;           // x tiles by cp.async (any T / alignment) instead of TMA
     int await_mode;          // how the MMA issuer waits for a converted tile (mbar_wait_mode)
+    uint32_t tile_scale;     // tile_bit() scale for the re-scan's tile map
     int own_shift;           // scan group of code tile nt = (nt >> own_shift) & 1: 0 = alternate tiles, 1 = alternate PAIRS of tiles
     int fwait_mode;          // how the front group waits for a free A buffer / a landed x stage (3: suspending wait + 500 / 64 ns sleeps)
     int pipe_issue;          // software-pipelined MMA issue loop (resident codebook, N = 128 batches)
@@ -101,9 +103,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // One arrival per WARP: every lane has finished its part (loads landed in registers, tcgen05.wait done, shared-memory
 // writes issued), __syncwarp orders those against lane 0, which arrives for all 32.  Per-thread arrivals serialise on
 // the barrier word: 2048 of them per tile cost ~4200 cycles, more than the MMAs (measured with tools/experiment.sh).
-__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {     // (lane passed in: re-reading SR_TID costs ~25 cycles)
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+    if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -398,8 +400,21 @@ __device__ __forceinline__ void issue_batch_n(int n_kb, uint32_t d_tmem, uint32_
             p.trace[(e) * p.trace_tiles + int(it_)] = clock64();                                  \
     } while (0)
 
-struct __align__(16) Cand { uint32_t k1, k2; int c1; uint32_t chains; };   // per frame, per scan group: best key, runner-up key, best's code,
-                                                                          // residue chains (bit j: column % 16 == j) that may hold the exact winner
+// Per frame, per scan group: best key, runner-up key, and two packed words for the back stage --
+//   w2 = best's code (24 bits) | chains[7:0] << 24,   w3 = tile map (24 bits) | chains[15:8] << 24
+// chains: residue chains (bit j: column % 16 == j) that may hold the exact winner; tile map: which of the group's code tiles may
+// (bit = tile_bit(index of the tile among the group's own tiles)).  Both only matter for frames that go to the exact re-scan.
+struct __align__(16) Cand { uint32_t k1, k2, w2, w3; };
+__device__ __forceinline__ int cand_code(const Cand& c) { return int(c.w2 & 0xFFFFFFu); }
+__device__ __forceinline__ uint32_t cand_chains(const Cand& c) { return (c.w2 >> 24) | ((c.w3 >> 24) << 8); }
+__device__ __forceinline__ uint32_t cand_tiles(const Cand& c) { return c.w3 & 0xFFFFFFu; }
+
+// bit of the 24-bit tile map for the oi-th code tile of a scan group: one tile per bit up to 24 own tiles, else proportional
+__host__ __device__ __forceinline__ uint32_t tile_bit(uint32_t oi, uint32_t scale) { return (oi * scale) >> 16; }
+inline uint32_t tile_scale_for(int n_code_tiles) {
+    const uint32_t n_own = uint32_t(n_code_tiles + 1) >> 1;
+    return n_own <= 24u ? 65536u : (24u * 65536u) / n_own;
+}
 
 struct __align__(16) Smem {           // control block placed after the data stages
     uint64_t x_full[XS], x_empty[XS];
@@ -835,22 +850,23 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             if (wq == 0) VQ_TRACE(7, j);
             const Cand ca = cand[(cb * 2 + 0) * TM + r], cc = cand[(cb * 2 + 1) * TM + r];
             const float2 st = rowstat[cb * TM + r];
-            mbar_arrive_warp(smem_u32(&ctl->cand_empty[cb]));
+            mbar_arrive_warp(smem_u32(&ctl->cand_empty[cb]), lane);
             const int n = wfin.n, t = wfin.t * TM + r;
             wfin.advance(step, p.tiles_per_utt);
             const bool in_tile = t < p.T;
             bool unsafe = false;
-            uint32_t cand_mask = 0xFFFFFFFFu;                 // bits 0-15: residue chains of scan group 0 (even code tiles), 16-31: group 1
+            uint32_t cand_mask = 0xFFFFFFFFu;                 // bits 0-15: residue chains of scan group 0, 16-31: group 1
+            uint2 tile_mask = make_uint2(0xFFFFFFu, 0xFFFFFFu);  // code tiles of group 0 / group 1 (see tile_bit())
             const int64_t row = int64_t(n) * p.T + t;
 #if VQ_EXPERIMENT & 256                   /* timing experiment: the back stage only shakes hands and stores a candidate */
-            if (in_tile) p.idx[row] = ca.c1 + int(st.x != 1.25f ? 0 : cc.c1);
+            if (in_tile) p.idx[row] = cand_code(ca) + int(st.x != 1.25f ? 0 : cand_code(cc));
             if (false) {
 #else
             if (in_tile) {
 #endif
                 const float xx = st.x, rr = st.y;
                 const bool a_wins = ca.k1 >= cc.k1;
-                const int c1 = a_wins ? ca.c1 : cc.c1;
+                const int c1 = a_wins ? cand_code(ca) : cand_code(cc);
                 const uint32_t kbest = max(ca.k1, cc.k1);
                 // every code other than c1 has a key <= kbound
                 const uint32_t kbound = __vimax3_u32(min(ca.k1, cc.k1), ca.k2, cc.k2);
@@ -902,8 +918,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     // group flagged the residue chains whose maximum clears its own (lower or equal) threshold, and a group
                     // whose best is out of reach contributes nothing.
                     const float reach = t_best - 2.f * err;
-                    cand_mask = (__uint_as_float(ca.k1) >= reach ? (ca.chains & 0xFFFFu) : 0u) |
-                                (__uint_as_float(cc.k1) >= reach ? (cc.chains << 16) : 0u);
+                    const bool a_in = __uint_as_float(ca.k1) >= reach, c_in = __uint_as_float(cc.k1) >= reach;
+                    cand_mask = (a_in ? cand_chains(ca) : 0u) | (c_in ? (cand_chains(cc) << 16) : 0u);
+                    // ... and of those, only the code tiles whose maximum came within reach of the group's running best
+                    tile_mask = make_uint2(a_in ? cand_tiles(ca) : 0u, c_in ? cand_tiles(cc) : 0u);
                 }
 #if VQ_EXPERIMENT & 4                     /* timing experiment: never take the fallback */
                 safe = true;
@@ -928,6 +946,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     const int pos = base + __popc(m & ((1u << lane) - 1u));
                     p.unsafe_rows[pos] = int(row);
                     p.unsafe_mask[pos] = cand_mask;              // which codes the exact re-scan has to look at
+                    p.unsafe_tiles[pos] = tile_mask;
                 }
             }
         };
@@ -980,7 +999,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                 }
 #endif
-                mbar_arrive_warp(smem_u32(&ctl->x_empty[s]));                      // the stage's data now lives in registers
+                mbar_arrive_warp(smem_u32(&ctl->x_empty[s]), lane);                      // the stage's data now lives in registers
                 tc_st16(a_tmem + uint32_t(ch * (XCH / 2)), pk);
             }
             const float xx = (xa[0] + xa[1]) + (xa[2] + xa[3]);
@@ -991,7 +1010,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             rowstat[rstat.i * TM + r] = make_float2(xx, rr);                   // read back by this same thread in finish()
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive_warp(smem_u32(&ctl->a_full[a]));
+            mbar_arrive_warp(smem_u32(&ctl->a_full[a]), lane);
             if (wq == 0) VQ_TRACE(5, it);
             if (it >= uint32_t(p.lag)) finish(it - p.lag);
         }
@@ -1001,6 +1020,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     } else if (warp < 12) {
         // ============================================================ scan groups (thread == frame)
         reg_inc<REGS_SCAN>();
+        // shared-window address of the control block, taken once (converting &ctl->bar[i] at every use re-reads SR_CgaCtaId,
+        // a ~30-cycle special-register read, several times per code tile on this group's critical path)
+        uint32_t ctl_s = smem_u32(ctl);
+        asm volatile("" : "+r"(ctl_s));                        // (opaque: keeps the compiler from re-deriving it at every use)
+#define VQ_BAR(member, i) (ctl_s + uint32_t(offsetof(Smem, member)) + uint32_t(i) * 8u)
         const int wq = warp & 3, r = wq * 32 + lane, wg = (warp - 4) >> 2;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
         uint32_t qa = 0, it = 0;
@@ -1017,6 +1041,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, rc.next(uint32_t(p.cd))) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
+            uint32_t tmap = 0u;                                    // HARD: this group's code tiles that may hold the exact winner
             uint32_t ch[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) ch[j] = 0u;
@@ -1035,7 +1060,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 // suspended wait with a back-off between probes: the probes of the eight scan warps were a third of all
                 // instructions the kernel issued (ncu), on schedulers they share with the front group and the issuer
-                mbar_wait_backoff(smem_u32(&ctl->acc_full[s]), sph, p.scan_sleep_ns);
+                mbar_wait_backoff(VQ_BAR(acc_full, s), sph, p.scan_sleep_ns);
                 tc_fence_after();
                 if (warp == 4 && nt == 0) VQ_TRACE(8, it);
                 if (warp == 4 || warp == 8) VQ_TRACE_NT(12, it, nt);
@@ -1058,9 +1083,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     //  measured equal on speech-like and 1.6 % slower on Gaussian latents: ptxas already gives every LDTM its own
                     //  scoreboard, so the scan of the first columns starts as soon as THEY have landed either way.)
                     tc_fence_before();
-                    mbar_arrive_warp(smem_u32(&ctl->acc_empty[s]));                // all 128 columns are in registers: free the stage
+                    mbar_arrive_warp(VQ_BAR(acc_empty, s), lane);                // all 128 columns are in registers: free the stage
                     if (warp == 4 || warp == 8) VQ_TRACE_NT(13, it, nt);
                 }
+                uint32_t tmx = 0u;                                 // HARD: this code tile's best key
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int cbase = nt * TN + half * 64;
@@ -1079,6 +1105,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     else if (p.hn_stream) scan64<1>(v0, v1, hn_s + (warp - 4) * 256 + hbuf + half * 64, ch, t1, t2, blk);
                     else scan64<0>(v0, v1, p.hn_off + cbase, ch, t1, t2, blk);
 #endif
+                    if (HARD) tmx = half == 0 ? t1 : max(tmx, t1);
                     // fold this half tile into the running pair: r1 = best key, r2 = best key outside the winner's block
                     if (t1 > r1) {
                         r2 = max(r1, t2);
@@ -1088,10 +1115,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         r2 = max(r2, t1);
                     }
                 }
+                if (HARD) {
+                    // A code of this tile can only be the exact winner if its FP16 score is within 2 err of the final best, hence of
+                    // the group's running best (which only grows): tiles whose maximum is not are never visited by the re-scan.
+                    // (2 err <= err_c[0] ||x||^2 + err_c[1], the a-priori bound; rowstat was written before the tile's first MMA.)
+                    const float gapf = fmaf(ctl->err_c[0], rowstat[rc.i * TM + r].x, ctl->err_c[1]);
+                    const uint32_t oi = p.own_shift ? ((uint32_t(nt) >> 2) << 1 | (uint32_t(nt) & 1u)) : (uint32_t(nt) >> 1);
+                    if (__uint_as_float(tmx) >= __uint_as_float(r1) - gapf) tmap |= 1u << tile_bit(oi, p.tile_scale);
+                }
                 if (warp == 4 || warp == 8) VQ_TRACE_NT(14, it, nt);
             }
             const uint32_t cb = rc.i, cph = rc.ph;
-            mbar_wait<0>(smem_u32(&ctl->cand_empty[cb]), cph ^ 1);
+            mbar_wait<0>(VQ_BAR(cand_empty, cb), cph ^ 1);
             r2 = max(r2, chains_runner_up(ch));                    // ... and outside the winner's residue chain: the exact runner-up
             int res = 0;                                           // the winner's residue: the chain that holds the maximum
 #pragma unroll
@@ -1110,9 +1145,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     for (int j = 0; j < 16; ++j) chains |= (__uint_as_float(ch[j]) >= reach) ? (1u << j) : 0u;
                 }
             }
-            Cand c; c.k1 = r1; c.k2 = r2; c.c1 = rc1 + res; c.chains = chains;
+            Cand c; c.k1 = r1; c.k2 = r2;
+            c.w2 = uint32_t(rc1 + res) | (chains << 24);
+            c.w3 = (HARD ? tmap : 0xFFFFFFu) | ((chains >> 8) << 24);
             cand[(cb * 2 + wg) * TM + r] = c;
-            mbar_arrive_warp(smem_u32(&ctl->cand_full[cb]));
+            mbar_arrive_warp(VQ_BAR(cand_full, cb), lane);
             if (warp == 4) VQ_TRACE(9, it);
         }
     } else {
@@ -1243,6 +1280,7 @@ inline const char* plan_assign_tc(int D, int K, tc::Params& p, size_t& smem) {
     // hand-off falls into the two batches the tensor core runs for the OTHER group.
     p.own_shift = (p.acc_stages == 3 && p.n_nt == 4) ? 1 : 0;
     if (tc_env().own >= 0 && p.own_shift) p.own_shift = tc_env().own != 0 ? 1 : 0;     // VQ_K1_OWN=0: alternate tiles (A/B switch)
+    p.tile_scale = tile_scale_for(p.n_nt);
     p.await_mode = tc_env().await >= 0 ? tc_env().await : 0;
     p.fwait_mode = tc_env().fwait >= 0 ? tc_env().fwait : 3;
     p.pipe_issue = tc_env().pipe != 0 ? 1 : 0;                  // VQ_K1_PIPE=0: the plain loop (A/B switch)
@@ -1302,7 +1340,7 @@ inline int launch_assign_tc(const XT* x, int64_t N, int D, int64_t T, const floa
     size_t smem = 0;
     if (const char* why = plan_assign_tc(D, K, p, smem)) return fail("vq_assign (tcgen05 path): %s", why);
     VQ_REQUIRE(p.Kp == w.Kp && p.Dp == w.Dp, "workspace was carved for another shape");
-    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.unsafe_mask = w.unsafe_mask;
+    p.x = x; p.k = k; p.ee = w.ee; p.hn = w.hn; p.hn_off = w.hn_off; p.hdr = w.hdr; p.unsafe_rows = w.unsafe_rows; p.unsafe_mask = w.unsafe_mask; p.unsafe_tiles = w.unsafe_tiles;
     p.idx = idx; p.min_d = min_d; p.scalars = scalars; p.dbg = dbg; p.trace = trace; p.trace_tiles = trace_tiles;
     p.N = int(N); p.T = int(T);
     p.x_cpasync = (sizeof(XT) == 4 && (T % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)) ? 1 : 0;

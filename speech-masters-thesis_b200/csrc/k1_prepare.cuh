@@ -25,6 +25,7 @@ struct AssignWorkspace {
     __half* eb;           // [Kp][Dp] FP16 image, zero padded
     int* unsafe_rows;     // [N*T] frames the tcgen05 kernel could not prove safe
     uint32_t* unsafe_mask;           // [N*T] per listed frame: residue chains (column % 16) x scan group whose codes the exact re-scan visits
+    uint2* unsafe_tiles;             // [N*T] ... and of those, which code tiles (24-bit map per scan group)
     int Kp, Dp;
     size_t bytes;
 };
@@ -45,6 +46,7 @@ inline AssignWorkspace carve_workspace(void* base, int64_t rows, int K, int D) {
     w.eb = reinterpret_cast<__half*>(p + off);              off += align256(size_t(w.Kp) * w.Dp * 2);
     w.unsafe_rows = reinterpret_cast<int*>(p + off);               off += align256(size_t(rows) * 4);
     w.unsafe_mask = reinterpret_cast<uint32_t*>(p + off);          off += align256(size_t(rows) * 4);
+    w.unsafe_tiles = reinterpret_cast<uint2*>(p + off);            off += align256(size_t(rows) * 8);
     w.bytes = off;
     return w;
 }

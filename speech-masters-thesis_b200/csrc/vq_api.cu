@@ -220,7 +220,8 @@ static int assign_impl(const XT* x, int64_t N, int64_t D, int64_t T, const float
         unsigned int* hint_dev = hard_hint(dev);               // (unified addressing: the mapped host pointer is valid on the device)
         auto launch_list = [&](auto kernel) {
             return cudaLaunchKernelEx(&cfg, kernel, x, N, int(D), T, k, (const float*)w.ee, K, n_code_tiles, own_shift, idx, min_d, scalars,
-                                      (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, w.hdr, hint_dev);
+                                      (const int*)w.unsafe_rows, (const uint32_t*)w.unsafe_mask, (const uint2*)w.unsafe_tiles,
+                                      tc::tile_scale_for(n_code_tiles), w.hdr, hint_dev);
         };
         if (vec && D <= 128) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 1, XT>));
         else if (vec) VQ_CUDA_OK(launch_list(assign_list_kernel<true, 4, XT>));

@@ -1,6 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_audit.py tests/test_gpu_parity.py -m gpu -x -q -k "every_row or sweep_corner or golden or random" 2>&1 | tail -3
-for o in 1 0; do echo "own $o: $(VQ_K1_OWN=$o python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so 2>&1 | tail -1)"; done | tee gpurun_out/experiment_own.log
-for o in 1 0; do echo "own $o gaussian: $(VQ_K1_OWN=$o python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so gaussian 2>&1 | tail -1)"; done | tee -a gpurun_out/experiment_own.log
-python tools/tc_timeline.py > gpurun_out/tl.log 2>&1; tail -33 gpurun_out/tl.log | head -17
+python tools/ab_k1.py ab/libvqb200_new.so ab/libvqb200_base.so speech-masters-thesis_b200/lib/libvqb200.so 2>&1 | tail -1 | tee gpurun_out/experiment_addr.log
+python tools/ab_k1.py ab/libvqb200_new.so ab/libvqb200_base.so speech-masters-thesis_b200/lib/libvqb200.so gaussian 2>&1 | tail -1 | tee -a gpurun_out/experiment_addr.log
+timeout 900 python -m pytest tests/test_gpu_audit.py tests/test_gpu_parity.py -m gpu -x -q -k "every_row or sweep_corner or golden or random or tcgen05_route or bf16" 2>&1 | tail -3
+timeout 600 python tools/sweep.py --gaussian --quick > gpurun_out/sweepg.log 2>&1; echo "sweepg rc=$?"
+python - <<'PY'
+import json
+for p in json.load(open('gpurun_out/sweep_gaussian.json'))['results']: print(p['K'],p['D'],round(p['frac_of_peak_main'],3),round(p['assign_main_ms'],4),round(p['fallback_ms'],4),round(p['unsafe_frac'],4),p['check'].get('mismatches'))
+PY
