@@ -46,7 +46,10 @@ def make_batch(n_utt, seed, clustered=True):
     import torch
     from oracle import vq_oracle as O          # synthetic-input recipe only; not on the timed path
     gen = torch.Generator().manual_seed(seed)
-    code = torch.randn(K_BINS, EMB, generator=gen)
+    torch.randn(K_BINS, EMB, generator=gen)     # (keeps rank 0's batch what it always was)
+    # ONE codebook for every rank: a rank whose latents cluster around another codebook than the one it quantises against
+    # (the replicas share rank 0's, bottleneck.py:41) sees an adversarial batch and drags the whole job onto the re-scan path
+    code = torch.randn(K_BINS, EMB, generator=torch.Generator().manual_seed(0))
     lengths = O.ljspeech_like_lengths(n_utt, gen)
     x, mask = O.synthetic_batch(lengths, EMB, gen, codebook=code if clustered else None)
     return x, mask, lengths, code

@@ -84,6 +84,10 @@ if __name__ == "__main__":
     summarise(os.path.join(g, "prof_k23.ncu-rep"),
               "K23_ONLY=k2_fwd,k3a K23_REPS=2 ncu --set full --clock-control none -k regex:'gather_async_kernel|ema_accumulate_runs' -s 6 -c 2 python tools/k23_bench.py",
               f"{TAG}_k2_k3_full_summary.json")
+    if os.path.exists(os.path.join(g, "prof_k3a.ncu-rep")):
+        summarise(os.path.join(g, "prof_k3a.ncu-rep"),
+                  "K23_ONLY=k3a K23_REPS=2 ncu --set full --clock-control none -k regex:ema_accumulate_runs -s 3 -c 1 python tools/k23_bench.py",
+                  f"{TAG}_k3a_full_summary.json")
     summarise(os.path.join(g, "prof_list.ncu-rep"),
               "ncu --set full --clock-control none -k regex:assign_list -c 1 python tools/list_debug.py   (i.i.d. Gaussian batch, 5576 frames re-scanned)",
               f"{TAG}_rescan_full_summary.json")

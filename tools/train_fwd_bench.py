@@ -31,10 +31,15 @@ def main():
     x, mask = O.synthetic_batch(lengths, D, gen, codebook=code)
     xd, md = x.to(dev), mask.to(dev)
     out = {"world": world, "p2p_env": os.environ.get("VQ_P2P", "1")}
-    for name, parity in (("device_rng", False), ("rng_parity", True)):
-        blk = vqb200.BottleneckBlock(K, D, 0.99, 1.0, rng_parity=parity).to(dev)
-        blk.k, blk.k_sum, blk.k_elem, blk.init = code.to(dev), (code * 4).to(dev), torch.full((K,), 4.0, device=dev), True
-        blk.train()
+    same_block = os.environ.get("TFB_SAME_BLOCK") == "1"       # bench.py's order: ONE block, rng_parity first, then the device RNG
+    order = (("rng_parity", True), ("device_rng", False)) if same_block else (("device_rng", False), ("rng_parity", True))
+    blk = None
+    for name, parity in order:
+        if blk is None or not same_block:
+            blk = vqb200.BottleneckBlock(K, D, 0.99, 1.0, rng_parity=parity).to(dev)
+            blk.k, blk.k_sum, blk.k_elem, blk.init = code.to(dev), (code * 4).to(dev), torch.full((K,), 4.0, device=dev), True
+            blk.train()
+        blk.rng_parity = parity
         for _ in range(3):
             blk(xd, md, update_k=True)
         torch.cuda.synchronize()
