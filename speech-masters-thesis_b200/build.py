@@ -36,6 +36,9 @@ def build(force=False, verbose=False):
     exp = os.environ.get("VQ_EXPERIMENT")
     if exp:
         flags = flags + [f"-DVQ_EXPERIMENT={int(exp)}"]
+    for knob in ("VQ_K3_WARPS", "VQ_K3_DW", "VQ_K3_STAGES", "VQ_K3_OCC"):       # build-time experiment knobs of K3a
+        if os.environ.get(knob):
+            flags = flags + [f"-D{knob}={int(os.environ[knob])}"]
     cmd = [NVCC] + flags + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

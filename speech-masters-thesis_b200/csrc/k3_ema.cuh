@@ -23,7 +23,19 @@ constexpr int E_THREADS = 256;
 // costs one update per tile instead of one per row.
 constexpr int ER_TT = 64;                    // frames per tile
 constexpr int ER_XS = ER_TT + 4;             // row stride (16-byte aligned rows)
-constexpr int ER_WARPS = 16;                 // warp 15 sorts, warps 0..14 accumulate
+#ifndef VQ_K3_WARPS
+#define VQ_K3_WARPS 16
+#endif
+#ifndef VQ_K3_DW
+#define VQ_K3_DW 64
+#endif
+#ifndef VQ_K3_STAGES
+#define VQ_K3_STAGES 5
+#endif
+#ifndef VQ_K3_OCC
+#define VQ_K3_OCC 1                          // CTAs per SM the launch aims for (build-time experiment knobs, see tools/experiment_k3.sh)
+#endif
+constexpr int ER_WARPS = VQ_K3_WARPS;        // the last warp sorts, the others accumulate
 constexpr int ER_THREADS = ER_WARPS * 32;
 constexpr int ER_PER = (ER_TT + ER_WARPS - 2) / (ER_WARPS - 1);   // sorted rows per accumulating warp (5)
 constexpr int ER_LIST = 256;                 // valid tiles compacted per pass
@@ -45,7 +57,7 @@ __global__ void __launch_bounds__(256) ema_tile_flags_kernel(const float* __rest
 }
 
 template <bool SLAB> struct ErCfg;
-template <> struct ErCfg<true>  { static constexpr int DW = 64,  STAGES = 5; };   // depth slice width, ring depth
+template <> struct ErCfg<true>  { static constexpr int DW = VQ_K3_DW,  STAGES = VQ_K3_STAGES; };   // depth slice width, ring depth
 template <> struct ErCfg<false> { static constexpr int DW = 128, STAGES = 6; };
 template <bool SLAB> constexpr int er_stage_bytes() { return ErCfg<SLAB>::DW * ER_XS * 4 + ER_TT * 8 + ER_TT * 4; }
 template <bool SLAB> inline size_t er_smem_bytes(int K) {
@@ -53,7 +65,7 @@ template <bool SLAB> inline size_t er_smem_bytes(int K) {
 }
 
 template <bool SLAB>
-__global__ void __launch_bounds__(ER_THREADS, 1)
+__global__ void __launch_bounds__(ER_THREADS, VQ_K3_OCC)
 ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ mask,
                            int64_t N, int D, int64_t T, int K, float* __restrict__ stats,
                            const unsigned char* __restrict__ tile_flags) {
@@ -277,6 +289,10 @@ ema_accumulate_runs_kernel(const float* __restrict__ x, const int64_t* __restric
 //  [TMA boxes + mbarrier ring, warp w owns code % 30 == w, one prep warp publishing per-owner frame masks]: 0.122 ms
 //  against 0.115 ms for the kernel above.  With idle consumers the same ring streams the valid tiles in 0.068 ms, i.e.
 //  2.8 TB/s: 64-frame tiles of a 64-deep slice are 256-byte pieces at a stride of T*4 bytes, which is what bounds both.)
+
+// (Also tried and measured in round 2, not kept: two CTAs per SM on 32-deep slices [VQ_K3_DW=32 VQ_K3_STAGES=4 VQ_K3_OCC=2] so
+//  that one CTA's per-tile barrier and sort hide behind the other's walk: 0.109 ms with 16 warps per CTA, 0.127 ms with 8,
+//  against 0.096 ms -- twice the slices means every tile's keys are sorted and walked twice as often per byte.)
 
 // (Also tried and measured, not kept: the whole shared memory as a six-stage TMA ring, two consumer warps per stage, groups
 //  of equal codes found with match.any and flushed as coalesced 128-byte reductions straight to L2 instead of a slab:

@@ -366,7 +366,7 @@ int vq_ema_accumulate(const float* x, const int64_t* idx, const float* mask, int
         // private [K][64] slab per (row chunk, 64-deep slice); one CTA per SM
         VQ_CUDA_OK(ensure_dynamic_smem(ema_accumulate_runs_kernel<true>, ER_DYN_SMEM_MAX));
         const int slices = int((D + ErCfg<true>::DW - 1) / ErCfg<true>::DW);
-        const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, num_sms() / slices)));
+        const int gx = int(std::min<int64_t>(tiles_r, std::max<int64_t>(1, VQ_K3_OCC * num_sms() / slices)));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx, slices);
         cfg.blockDim = dim3(ER_THREADS);
