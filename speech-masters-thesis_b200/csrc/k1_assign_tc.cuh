@@ -435,7 +435,7 @@ inline size_t handoff_bytes(int cd) { return size_t(cd) * (2 * TM * sizeof(Cand)
 // in the scan groups costs ~5 % just by being there), and speech-like batches never need them: HARD = false bounds the residual
 // a priori and lets the rare unsafe frame be re-scanned over all codes.  The host picks the variant from a hint the re-scan
 // kernel leaves in mapped host memory (see hard_hint() below).
-template <bool RESCORE, bool HARD, typename XT>
+template <bool RESCORE, bool HARD, bool FOLD, typename XT>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1037,7 +1037,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(hn_s + (warp - 4) * 256 + buf + lane * 4)),
                          "l"(p.hn_off + size_t(nt_) * TN + lane * 4) : "memory");
         };
-        if (p.hn_stream && wg < p.n_nt) stage_offsets(wg, 0u);
+        if (!FOLD && p.hn_stream && wg < p.n_nt) stage_offsets(wg, 0u);
         for (int tile = first; tile < p.n_tiles; tile += step, ++it, rc.next(uint32_t(p.cd))) {
             uint32_t r1 = 0u, r2 = 0u;
             int rc1 = 0;
@@ -1052,8 +1052,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 if (((uint32_t(nt) >> p.own_shift) & 1u) != uint32_t(wg)) continue;
                 const uint32_t s = rs.i, sph = rs.ph;
                 // buffer of this warp's pair (as a float offset, 0 or TN): parity of the number of code tiles this group has scanned
-                const uint32_t hbuf = p.hn_stream ? ((it * uint32_t((p.n_nt - wg + 1) >> 1) + uint32_t(nt >> 1)) & 1u) * uint32_t(TN) : 0u;
-                if (p.hn_stream) {
+                const uint32_t hbuf = (!FOLD && p.hn_stream) ? ((it * uint32_t((p.n_nt - wg + 1) >> 1) + uint32_t(nt >> 1)) & 1u) * uint32_t(TN) : 0u;
+                if (!FOLD && p.hn_stream) {
                     asm volatile("cp.async.wait_all;" ::: "memory");               // this tile's offsets (issued one tile ago) have landed
                     __syncwarp();                                                  // ... for every lane, and the other buffer is no longer read
                     stage_offsets(nt + 2 < p.n_nt ? nt + 2 : wg, hbuf ^ uint32_t(TN));       // (wraps to the next frame tile's first code tile)
@@ -1100,7 +1100,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     __nanosleep(200);
 #endif
 #else
-                    if (p.fold) scan64<2>(v0, v1, nullptr, ch, t1, t2, blk);
+                    if (FOLD) scan64<2>(v0, v1, nullptr, ch, t1, t2, blk);
                     else if (p.hn_in_smem) scan64<1>(v0, v1, hn_s + cbase, ch, t1, t2, blk);
                     else if (p.hn_stream) scan64<1>(v0, v1, hn_s + (warp - 4) * 256 + hbuf + half * 64, ch, t1, t2, blk);
                     else scan64<0>(v0, v1, p.hn_off + cbase, ch, t1, t2, blk);
@@ -1391,10 +1391,16 @@ inline int launch_assign_tc(const XT* x, int64_t N, int D, int64_t T, const floa
         kernel<<<grid, THREADS, smem, stream>>>(x_map, b_map, p);
         return cudaGetLastError();
     };
-    if (rescore && hard) VQ_CUDA_OK(launch(assign_tc_kernel<true, true, XT>));
-    else if (rescore) VQ_CUDA_OK(launch(assign_tc_kernel<true, false, XT>));
-    else if (hard) VQ_CUDA_OK(launch(assign_tc_kernel<false, true, XT>));
-    else VQ_CUDA_OK(launch(assign_tc_kernel<false, false, XT>));
+    // (FOLD is a template parameter so that the scan groups' loop carries one scan body instead of four behind run-time branches)
+    auto launch_f = [&](auto fold_tag) -> cudaError_t {
+        constexpr bool F = decltype(fold_tag)::value;
+        if (rescore && hard) return launch(assign_tc_kernel<true, true, F, XT>);
+        if (rescore) return launch(assign_tc_kernel<true, false, F, XT>);
+        if (hard) return launch(assign_tc_kernel<false, true, F, XT>);
+        return launch(assign_tc_kernel<false, false, F, XT>);
+    };
+    if (p.fold) VQ_CUDA_OK(launch_f(std::true_type()));
+    else VQ_CUDA_OK(launch_f(std::false_type()));
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -1,7 +1,10 @@
 #!/bin/bash
-# K3a occupancy experiment: 2 CTAs per SM with 32-deep slices (build-time knobs), A/B against the product
 mkdir -p gpurun_out
-for l in "" ab/libvqb200_k3a.so ab/libvqb200_k3b.so; do
-  echo "lib=${l:-product}: $(VQB200_LIB=${l:+$PWD/$l} K23_ONLY=k3a python tools/k23_bench.py 2>&1 | tail -1 | cut -c1-300)"
-done | tee gpurun_out/experiment_k3a.log
-VQB200_LIB=$PWD/ab/libvqb200_k3a.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ema or golden or random" 2>&1 | tail -2
+python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so ab/libvqb200_prev.so 2>&1 | tail -1 | tee gpurun_out/experiment_foldtpl.log
+python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so ab/libvqb200_prev.so gaussian 2>&1 | tail -1 | tee -a gpurun_out/experiment_foldtpl.log
+timeout 900 python -m pytest tests/test_gpu_audit.py tests/test_gpu_parity.py -m gpu -x -q -k "every_row or sweep_corner or golden or random or tcgen05_route or bf16" 2>&1 | tail -3
+timeout 600 python tools/sweep.py --quick > gpurun_out/sweepq.log 2>&1; echo "sweep rc=$?"
+python - <<'PY'
+import json
+for p in [q for q in json.load(open('gpurun_out/sweep.json'))['results'] if 'frac_of_peak_main' in q]: print(p['K'],p['D'],round(p['frac_of_peak_main'],3),round(p['assign_main_ms'],4),p['check'].get('mismatches'))
+PY
