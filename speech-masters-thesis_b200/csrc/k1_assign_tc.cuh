@@ -391,12 +391,12 @@ __device__ __forceinline__ void issue_batch_n(int n_kb, uint32_t d_tmem, uint32_
 // timeline probe: event e of local tile `it` of CTA 0
 #define VQ_TRACE_NT(e, it_, nt_)                                                                  \
     do {                                                                                          \
-        if (p.trace && blockIdx.x == 0 && lane == 0 && int(it_) >= 8 && int(it_) < 16 && p.trace_tiles >= 32 && p.n_nt == 4) \
+        if (TRACE && p.trace && blockIdx.x == 0 && lane == 0 && int(it_) >= 8 && int(it_) < 16 && p.trace_tiles >= 32 && p.n_nt == 4) \
             p.trace[(e) * p.trace_tiles + (int(it_) - 8) * 4 + int(nt_)] = clock64();             \
     } while (0)
 #define VQ_TRACE(e, it_)                                                                          \
     do {                                                                                          \
-        if (p.trace && blockIdx.x == 0 && lane == 0 && int(it_) < p.trace_tiles)                  \
+        if (TRACE && p.trace && blockIdx.x == 0 && lane == 0 && int(it_) < p.trace_tiles)          \
             p.trace[(e) * p.trace_tiles + int(it_)] = clock64();                                  \
     } while (0)
 
@@ -435,7 +435,7 @@ inline size_t handoff_bytes(int cd) { return size_t(cd) * (2 * TM * sizeof(Cand)
 // in the scan groups costs ~5 % just by being there), and speech-like batches never need them: HARD = false bounds the residual
 // a priori and lets the rare unsafe frame be re-scanned over all codes.  The host picks the variant from a hint the re-scan
 // kernel leaves in mapped host memory (see hard_hint() below).
-template <bool RESCORE, bool HARD, bool FOLD, typename XT>
+template <bool RESCORE, bool HARD, bool FOLD, bool TRACE, typename XT>
 __global__ void __launch_bounds__(THREADS, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -707,7 +707,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                             __syncwarp();
                             VQ_TRACE_NT(11, it, nt);
-                            if (p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
+                            if (TRACE && p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
                                 mbar_spin(smem_u32(&ctl->acc_full[0]), sph);
                                 VQ_TRACE_NT(15, it, nt);
                             }
@@ -728,7 +728,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                             __syncwarp();
                             VQ_TRACE_NT(11, it, nt);
-                            if (p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
+                            if (TRACE && p.trace && p.trace_tiles >= 64) {       // probe only: when does the ISSUER see the batch complete?
                                 mbar_spin(smem_u32(&ctl->acc_full[st]), sph);
                                 VQ_TRACE_NT(15, it, nt);
                             }
@@ -1156,7 +1156,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         reg_dec<REGS_ISSUER>();                                     // W_ALLOC: idle until the end
         // (timeline runs only: this warp watches the accumulator barriers of CTA 0 with a non-suspending probe and records when
         //  every MMA batch really completes -- the scan groups' own time stamps include their wake-up latency)
-        if (p.trace && blockIdx.x == 0 && p.n_nt == 4 && p.trace_tiles == 32 && !p.pair) {
+        if (TRACE && p.trace && blockIdx.x == 0 && p.n_nt == 4 && p.trace_tiles == 32 && !p.pair) {
             Ring rs;
             uint32_t it = 0;
             for (int tile = first; tile < p.n_tiles; tile += step, ++it)
@@ -1392,15 +1392,27 @@ inline int launch_assign_tc(const XT* x, int64_t N, int D, int64_t T, const floa
         return cudaGetLastError();
     };
     // (FOLD is a template parameter so that the scan groups' loop carries one scan body instead of four behind run-time branches)
-    auto launch_f = [&](auto fold_tag) -> cudaError_t {
-        constexpr bool F = decltype(fold_tag)::value;
-        if (rescore && hard) return launch(assign_tc_kernel<true, true, F, XT>);
-        if (rescore) return launch(assign_tc_kernel<true, false, F, XT>);
-        if (hard) return launch(assign_tc_kernel<false, true, F, XT>);
-        return launch(assign_tc_kernel<false, false, F, XT>);
+    // (... and the clock64 probes of tools/tc_timeline.py only exist in the TRACE instantiations -- FP32 latents only: their
+    //  predicated-off tests were ~20 issued instructions per code tile in the scan groups)
+    auto launch_f = [&](auto fold_tag, auto trace_tag) -> cudaError_t {
+        constexpr bool F = decltype(fold_tag)::value, TR = decltype(trace_tag)::value;
+        if (rescore && hard) return launch(assign_tc_kernel<true, true, F, TR, XT>);
+        if (rescore) return launch(assign_tc_kernel<true, false, F, TR, XT>);
+        if (hard) return launch(assign_tc_kernel<false, true, F, TR, XT>);
+        return launch(assign_tc_kernel<false, false, F, TR, XT>);
     };
-    if (p.fold) VQ_CUDA_OK(launch_f(std::true_type()));
-    else VQ_CUDA_OK(launch_f(std::false_type()));
+    if (trace) {
+        if constexpr (sizeof(XT) == 4) {
+            if (p.fold) VQ_CUDA_OK(launch_f(std::true_type(), std::true_type()));
+            else VQ_CUDA_OK(launch_f(std::false_type(), std::true_type()));
+        } else {
+            return fail("vq_assign_debug: the timeline probes need FP32 latents%s", "");
+        }
+    } else if (p.fold) {
+        VQ_CUDA_OK(launch_f(std::true_type(), std::false_type()));
+    } else {
+        VQ_CUDA_OK(launch_f(std::false_type(), std::false_type()));
+    }
     VQ_CUDA_OK(cudaGetLastError());
     return 0;
 }
