@@ -1,6 +1,8 @@
 #!/bin/bash
+# final validation on one GPU: the whole GPU test suite, both bench arms, smoke
 mkdir -p gpurun_out
-python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so ab/libvqb200_prev.so 2>&1 | tail -1 | tee gpurun_out/experiment_tracetpl.log
-python tools/ab_k1.py speech-masters-thesis_b200/lib/libvqb200.so ab/libvqb200_prev.so gaussian 2>&1 | tail -1 | tee -a gpurun_out/experiment_tracetpl.log
-timeout 900 python -m pytest tests/test_gpu_audit.py tests/test_gpu_parity.py -m gpu -x -q -k "every_row or sweep_corner or golden or random or tcgen05_route or bf16" 2>&1 | tail -3
-python tools/tc_timeline.py > gpurun_out/tl.log 2>&1; tail -34 gpurun_out/tl.log | head -10
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
+timeout 1200 python tools/sweep.py > gpurun_out/sweep.log 2>&1; echo "sweep rc=$?"
