@@ -450,7 +450,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     float* hn_s = reinterpret_cast<float*>(tail);                   // [Kp] when hn_in_smem and not folded
     uint8_t* hn_b = tail;                                           // [n_nt][4 KB] when folded
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle tells the compiler that the warp index is warp-uniform: role dispatch and everything derived from it can live
+    //  in uniform registers instead of being re-derived from SR_TID in the scan groups' loop)
+    const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const float e_norm_max = __uint_as_float(p.hdr->e_norm_max_bits);
     const KeySpace ks = make_key_space(e_norm_max);
 
