@@ -3,19 +3,23 @@
 //
 // One persistent CTA per SM, 16 warps, warp-specialised; after the prologue the register file is re-split with setmaxnreg
 // (issuers 40, front group 120, scan groups 176 registers per thread):
-//   warp 12       TMA producer for x: FP32 [32 depth x 128 frames] boxes straight out of the NCT tensor
+//   warp 12       TMA producer for x: FP32 or BF16 [32 depth x 128 frames] boxes straight out of the NCT tensor (4-byte
+//                 cp.async instead when T % 4 != 0 or the base is misaligned)
 //   warp 13       MMA issuer (one lane): tcgen05.mma kind::f16, A (frames x depth, FP16) from TMEM, B (codes x depth,
 //                 FP16, 128B-swizzled K-major) from shared memory, FP32 accumulators in TMEM: two 128-column stages filled
 //                 by N = 256 instructions, or (64 < D <= 128) three stages filled by N = 128 instructions; in the resident
 //                 steady state a tile's MMAs are straight-line code
 //   warp 14       TMA producer for the FP16 codebook image (resident in shared memory when it fits, else a ring)
-//   warp 15       TMEM allocator
+//   warp 15       TMEM allocator (in the TRACE instantiations: observer of the accumulator barriers for tools/tc_timeline.py)
 //   warps 0-3     front/back group: (front) FP32 smem tile -> FP16 pairs -> tcgen05.st into a TMEM A buffer
-//                 (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and
-//                 the FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) a few tiles later: merge the two
-//                 scan groups' candidates, run the provable safety test, write idx (optionally re-score in FP32)
-//   warps 4-11    scan groups (thread == frame; the two groups take alternate 128-code tiles): tcgen05.ld a WHOLE
-//                 accumulator stage into registers, hand the stage back to the tensor core, then scan it
+//                 (thread == frame, so the NCT -> row-major transpose is free) while measuring ||x||^2 and (HARD
+//                 instantiations) the FP16 rounding residual ||x - fp16(x)||^2 per frame; (back) a few tiles later: merge
+//                 the two scan groups' candidates, run the provable safety test, write idx (optionally re-score in FP32)
+//   warps 4-11    scan groups (thread == frame; the two groups take alternate 128-code tiles, or alternate PAIRS of
+//                 tiles, see plan_assign_tc): tcgen05.ld a WHOLE accumulator stage into registers, hand the stage back
+//                 to the tensor core, then scan it.  These eight warps pace the kernel (tools/tc_timeline.py): every
+//                 instruction in their loop costs 4-7 cycles, which is why everything they do not need at run time
+//                 is a template parameter (FOLD, HARD, TRACE).
 //
 // Keys.  The score of code c for frame r is s = x.e_c - ||e_c||^2/2 (argmax s == argmin distance).  The accumulator holds
 // t = acc - (||e_c||^2/2 - B) (the offset rides in the MMA as one extra k-step when the codebook is resident), with
@@ -27,8 +31,9 @@
 // Exactness: FP16 operands only SHORTLIST.  A frame keeps the shortlisted code iff the best key beats the runner-up by
 // more than twice a rigorous bound on the FP16 error,
 //     s1 - s2 > 2 (||x - x16|| max||e16|| + ||x|| max||e - e16|| + slack),
-// which proves it is the exact-arithmetic argmax; every other frame goes to a worklist that the exact FP32 kernel
-// (k1_assign_simt.cuh, LIST mode) re-scans.  The output therefore never depends on reduced-precision arithmetic.
+// which proves it is the exact-arithmetic argmax; every other frame goes to a worklist -- together with a mask of the
+// residue chains and a map of the code tiles that can still hold the winner (HARD instantiations) -- that the exact FP32
+// kernel (assign_list_kernel, k1_assign_simt.cuh) re-scans.  The output therefore never depends on reduced-precision arithmetic.
 #pragma once
 #include <cstddef>
 #include <cuda.h>
