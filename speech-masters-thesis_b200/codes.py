@@ -9,8 +9,9 @@ quantiser runs at GPU speed that loop is all ``.cpu()`` + ``.tolist()`` + pickle
   pinned host memory, 2 bytes per VALID frame over PCIe (the reference moves 8 per padded frame and then slices);
 * ``CodeShardWriter`` / ``CodeShard`` -- one binary file per shard: header, per-utterance lengths and offsets, all codes
   as one ``uint16`` array (optionally the audio as one ``float32`` array); memory-mapped on load;
-* ``CodeShard.item(i)`` yields what ``VQLatent.__getitem__`` unpickles (``{"x": [...], "q": [...]}``), and
-  ``export_pickles`` writes the reference's own directory layout, so ``datasets/vqlatent.py`` keeps working unchanged.
+* ``CodeShard.item(i)`` yields what ``VQLatent.__getitem__`` unpickles (``{"x": [...], "q": [...]}``),
+  ``export_pickles`` writes the reference's own directory layout, so ``datasets/vqlatent.py`` keeps working unchanged, and
+  ``CodeShard.from_pickles`` migrates an existing dump of the reference into a shard.
 """
 import ctypes
 import json
@@ -160,6 +161,28 @@ class CodeShard:
 
     def metadata(self):
         return {"compression_factor": self.compression_factor, "vocab_size": self.vocab_size}
+
+    @staticmethod
+    def from_pickles(dump_dir, split, path, keep_audio=True):
+        """Migrate an existing reference dump (``{split}/NNNNN.pkl`` + ``metadata.json``, generate_vq_dataset.py:86-89,216-220)
+        into one shard at ``path``.  Files are taken in name order (the order ``VQLatent`` indexes them in); codes must fit
+        ``uint16`` (``vocab_size`` <= 65 536).  Returns the opened shard."""
+        with open(os.path.join(dump_dir, "metadata.json")) as f:
+            meta = json.load(f)
+        if int(meta["vocab_size"]) > 65536:
+            raise ValueError("codes of this dump do not fit uint16")
+        writer = CodeShardWriter(path, meta["vocab_size"], meta.get("compression_factor", 128))
+        names = sorted(n for n in os.listdir(os.path.join(dump_dir, split)) if n.endswith(".pkl"))
+        for name in names:
+            with open(os.path.join(dump_dir, split, name), "rb") as f:
+                item = pickle.load(f)
+            q = np.asarray(item["q"], dtype=np.int64).reshape(-1)
+            if q.size and (q.min() < 0 or q.max() >= int(meta["vocab_size"])):
+                raise ValueError(f"{name}: code outside [0, vocab_size)")
+            audio = [np.asarray(item.get("x", []), dtype=np.float32)] if keep_audio else None
+            writer.append_batch(q.astype(np.uint16), [q.size], audio=audio)
+        writer.close()
+        return CodeShard(path)
 
     def export_pickles(self, dump_dir, split, start_index=0):
         """The reference's own layout (``{split}/NNNNN.pkl`` + ``metadata.json``, generate_vq_dataset.py:86-89,216-220),

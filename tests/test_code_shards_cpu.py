@@ -51,3 +51,36 @@ def test_shard_round_trip_matches_the_pickle_format(tmp_path):
     s2 = vqb200.CodeShard(str(tmp_path / "codes_only.vqb2"))
     assert s2[1]["q"] == q[1, :ql[1]].tolist() and s2[1]["x"] == [] and s2.audio is None
     assert os.path.getsize(tmp_path / "codes_only.vqb2") < 64 + n * 12 + 8 + 2 * int(ql.sum()) + 16
+
+
+def test_migrating_a_reference_dump(tmp_path):
+    """generate_vq_dataset.py's layout -> one shard -> the same items, in the order VQLatent indexes them."""
+    import json
+    import pickle
+    import numpy as np
+    from vqb200 import CodeShard
+    rng = np.random.default_rng(3)
+    dump = tmp_path / "dump"
+    (dump / "train").mkdir(parents=True)
+    items = []
+    for i in range(7):
+        n = int(rng.integers(1, 40))
+        item = {"x": rng.standard_normal(n * 128).astype(np.float32).tolist(), "q": rng.integers(0, 512, n).tolist()}
+        items.append(item)
+        with open(dump / "train" / f"{i:05d}.pkl", "wb") as f:
+            pickle.dump(item, f)
+    with open(dump / "metadata.json", "w") as f:
+        json.dump({"compression_factor": 128, "vocab_size": 512}, f)
+    shard = CodeShard.from_pickles(str(dump), "train", str(tmp_path / "train.vqb2"))
+    assert len(shard) == 7 and shard.metadata() == {"compression_factor": 128, "vocab_size": 512}
+    for i, item in enumerate(items):
+        got = shard.item(i)
+        assert got["q"] == item["q"]
+        assert np.allclose(got["x"], item["x"])
+    no_audio = CodeShard.from_pickles(str(dump), "train", str(tmp_path / "codes_only.vqb2"), keep_audio=False)
+    assert no_audio.item(3) == {"x": [], "q": items[3]["q"]}
+    # and back: the exported files are what the reference's reader unpickles
+    shard.export_pickles(str(tmp_path / "again"), "train")
+    with open(tmp_path / "again" / "train" / "00002.pkl", "rb") as f:
+        back = pickle.load(f)
+    assert back["q"] == items[2]["q"]
