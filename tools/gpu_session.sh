@@ -1,3 +1,7 @@
 #!/bin/bash
+# final validation on one GPU: the whole GPU test suite, both bench arms, smoke
 mkdir -p gpurun_out
-python tools/ab_k1.py ab/libvqb200_i24_s184.so ab/libvqb200_prev.so 2>&1 | tail -1 | tee gpurun_out/experiment_regs.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
